@@ -1,0 +1,243 @@
+/* jtrace_b200.h -- C ABI of libjtrace_b200.so, the B200 drop-in for julia-raytracer's
+ * per-pixel render loop.
+ *
+ * The reference has no FFI; the seam is the single call site
+ *     src/jtrace.jl:85-94  ->  trace_samples(state, scene, bvh, lights, params, ...)   (src/trace.jl:215)
+ * and the objects that call consumes. Every entry point below names the reference interface
+ * it replaces. All functions return 0 on success or a negative jt_status; the message is
+ * available from jt_last_error() (thread-local). No C++ exception, exit() or callback ever
+ * crosses this boundary. The library never keeps a host pointer after a call returns.
+ *
+ * Conventions (identical to the Julia side, converted inside the library):
+ *   - ids are 1-based, "none" is -1                      (src/scene.jl:45, :95-96)
+ *   - vertex/element indices are Int64                   (src/math.jl:15-20)
+ *   - the struct layouts are the ones Julia uses for the corresponding isbits structs, so a
+ *     Vector{BvhNode}, Vector{InstanceData}, Vector{MaterialData}, ... is passed zero-copy
+ *     with `pointer(v)` under GC.@preserve                
+ *   - images are row-major, idx = W*j + i, RGBA linear float   (src/trace.jl:598, :631-648)
+ */
+#ifndef JTRACE_B200_H
+#define JTRACE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JT_API __attribute__((visibility("default")))
+
+typedef enum {
+  JT_OK = 0,
+  JT_ERR_INVALID = -1,     /* bad argument / inconsistent scene description */
+  JT_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+  JT_ERR_NO_DEVICE = -3,   /* no CUDA device: there is no CPU fallback */
+  JT_ERR_UNSUPPORTED = -4, /* feature that also crashes the reference */
+  JT_ERR_NCCL = -5,
+  JT_ERR_INTERNAL = -6
+} jt_status;
+
+/* ---- reference data layouts -------------------------------------------------------------- */
+
+/* Frame3f = SVector{4,Vec3f}: columns x, y, z, o (src/math.jl:46) -- 48 B */
+typedef struct { float x[3], y[3], z[3], o[3]; } jt_frame;
+
+/* BvhNode (src/bvh.jl:34-39) -- 40 B */
+typedef struct {
+  float bbox_min[3], bbox_max[3];
+  int64_t start;     /* 1-based: first child (children are start, start+1) or first primitive slot */
+  int16_t num;
+  int8_t axis;       /* 1..3 */
+  uint8_t internal;  /* Bool */
+  uint8_t _pad[4];
+} jt_bvh_node;
+
+/* BvhTree (src/bvh.jl:46-49) */
+typedef struct {
+  const jt_bvh_node* nodes;
+  int64_t num_nodes;
+  const int64_t* primitives; /* 1-based element / instance ids */
+  int64_t num_primitives;
+} jt_bvh_desc;
+
+/* InstanceData (src/scene.jl:88-91) -- 64 B */
+typedef struct { jt_frame frame; int64_t shape; int64_t material; } jt_instance;
+
+/* MaterialData (src/scene.jl:213-229) -- 104 B; type = MaterialType enum 0..7 (src/scene.jl:191-200) */
+typedef struct {
+  int32_t type;
+  float emission[3], color[3];
+  float roughness, metallic, ior;
+  float scattering[3];
+  float scanisotropy, trdepth, opacity;
+  int64_t emission_tex, color_tex, roughness_tex, scattering_tex, normal_tex;
+} jt_material;
+
+/* EnvironmentData (src/scene.jl:117-120) -- 72 B */
+typedef struct { jt_frame frame; float emission[3]; int32_t _pad; int64_t emission_tex; } jt_environment;
+
+/* CameraData without the name (src/scene.jl:48-56); not isbits in Julia -> filled field by field */
+typedef struct {
+  jt_frame frame;
+  int32_t orthographic;
+  float lens, film, aspect, focus, aperture;
+} jt_camera;
+
+/* TextureData (src/scene.jl:146-151): exactly one of pixelsf / pixelsb is non-NULL */
+typedef struct {
+  int64_t width, height;
+  int32_t linear;
+  int32_t _pad;
+  const float* pixelsf;   /* Vec4f per texel, row-major, top row first */
+  const uint8_t* pixelsb; /* Vec4b per texel */
+} jt_texture_desc;
+
+/* ShapeData (src/shape.jl:13-23) + its ShapeBvh (src/bvh.jl:51-55).
+ * points / lines / radius / tangents are not accepted: they crash the reference. */
+typedef struct {
+  const float* positions;  int64_t num_positions;  /* Vec3f */
+  const float* normals;    int64_t num_normals;    /* Vec3f, 0 = none */
+  const float* texcoords;  int64_t num_texcoords;  /* Vec2f, 0 = none */
+  const float* colors;     int64_t num_colors;     /* Vec4f, 0 = none */
+  const int64_t* triangles; int64_t num_triangles; /* SVector{3,Int64}, 1-based */
+  const int64_t* quads;     int64_t num_quads;     /* SVector{4,Int64}, 1-based */
+  jt_bvh_desc bvh;
+} jt_shape_desc;
+
+/* TraceLight (src/trace.jl:102-105) */
+typedef struct {
+  int64_t instance;     /* 1-based or -1 */
+  int64_t environment;  /* 1-based or -1 */
+  const float* elements_cdf;
+  int64_t num_elements;
+} jt_light_desc;
+
+/* SceneData + SceneBvh + TraceLights: everything trace_samples reads (src/trace.jl:215-224) */
+typedef struct {
+  int64_t num_cameras;      const jt_camera* cameras;
+  int64_t num_instances;    const jt_instance* instances;
+  int64_t num_environments; const jt_environment* environments;
+  int64_t num_shapes;       const jt_shape_desc* shapes;
+  int64_t num_textures;     const jt_texture_desc* textures;
+  int64_t num_materials;    const jt_material* materials;
+  int64_t num_lights;       const jt_light_desc* lights;
+  jt_bvh_desc bvh;          /* SceneBvh.bvh: the TLAS over instances */
+  /* srgb_to_rgb(b / 255f0) for b = 0..255 computed by the host (src/color.jl:12-23): only 256
+   * distinct inputs exist, so a host-built table is bit-identical to the per-texel call in
+   * lookup_texture (src/scene.jl:836-849). NULL = the library computes it in double. */
+  const float* srgb_to_rgb_lut;
+} jt_scene_desc;
+
+/* Params fields read inside the hot path (src/cli.jl:90-108) + GPU extras */
+typedef struct {
+  int32_t camera;       /* 1-based index after find_camera (src/jtrace.jl:61) */
+  int32_t resolution;
+  int32_t samples;
+  int32_t bounces;
+  int32_t sampler;      /* 1 = path, 2 = naive (src/cli.jl:88, :111-116) */
+  int32_t clamp;        /* Params.clamp::Int (src/cli.jl:105) */
+  int32_t nocaustics;
+  int32_t envhidden;
+  int32_t tentfilter;
+  int32_t batch;
+  int32_t bvhstacksize; /* accepted, unused: traversal stacks live in registers/local memory */
+  int32_t traversal;    /* 0 = quantised wide BVH (fast), 1 = reference binary BVH, reference order */
+  uint64_t seed;        /* counter-based RNG seed (jt_rng.h) */
+  int32_t accumulate;   /* 0 = running-mean lerp exactly like src/trace.jl:631-647 (Q13)
+                           1 = plain sums (divide at download) -- what multi-GPU sharding reduces */
+  int32_t _reserved[7];
+} jt_params;
+
+/* Ray3f (src/geometry.jl:36-40) -- 32 B */
+typedef struct { float o[3], d[3], tmin, tmax; } jt_ray;
+
+/* SceneIntersection (src/shape.jl:61-66) -- 32 B; miss = {-1,-1,(0,0),0,false} */
+typedef struct { int64_t instance, element; float uv[2]; float distance; uint8_t hit; uint8_t _pad[3]; } jt_hit;
+
+/* Work counters accumulated by the render kernels since creation / last reset. */
+typedef struct {
+  uint64_t camera_paths;      /* trace_sample calls */
+  uint64_t scene_rays;        /* intersect_scene_bvh calls   (src/trace.jl:298,490) */
+  uint64_t light_rays;        /* intersect_instance_bvh calls (src/trace.jl:1025) */
+  uint64_t kernel_launches;   /* CUDA kernels launched by the library */
+  uint64_t _reserved[4];
+} jt_counters;
+
+typedef struct jt_scene jt_scene; /* device-resident scene: SceneData + SceneBvh + TraceLights */
+typedef struct jt_state jt_state; /* device-resident TraceState (src/trace.jl:87-96) */
+
+/* ---- library ------------------------------------------------------------------------------ */
+JT_API const char* jt_last_error(void);
+JT_API const char* jt_version(void);
+JT_API int jt_device_count(void);
+
+/* ---- scene: replaces handing (scene, bvh, lights) to trace_samples ------------------------- */
+/* Copies the whole description to `device` and builds the wide BVH from the given binary BVH. */
+JT_API int jt_scene_create(const jt_scene_desc* desc, int device, jt_scene** out);
+JT_API void jt_scene_destroy(jt_scene* scene);
+JT_API int jt_scene_counters(jt_scene* scene, jt_counters* out, int reset);
+/* Structural statistics of the device layout (for DESIGN.md / bench reporting). */
+typedef struct {
+  int64_t wide_nodes, wide_node_bytes, prim_records, prim_record_bytes;
+  int64_t inlined_instances, instanced_instances, texture_bytes, total_device_bytes;
+  int64_t _reserved[8];
+} jt_scene_stats;
+JT_API int jt_scene_get_stats(jt_scene* scene, jt_scene_stats* out);
+
+/* ---- state: make_trace_state (src/trace.jl:189-213) ---------------------------------------- */
+JT_API int jt_state_create(jt_scene* scene, const jt_params* params, jt_state** out);
+JT_API void jt_state_destroy(jt_state* state);
+JT_API int jt_state_size(jt_state* state, int32_t* width, int32_t* height, int32_t* samples);
+JT_API int jt_state_reset(jt_state* state);
+/* Copy the accumulators to the host in the reference's layouts (state.image :: Vector{Vec4f},
+ * albedo / normal :: Vector{Vec3f}, hits :: Vector{Int64}); any pointer may be NULL.
+ * In accumulate = 1 mode the sums are divided by `state.samples` first. */
+JT_API int jt_state_download(jt_state* state, float* image_rgba, float* albedo_rgb,
+                             float* normal_rgb, int64_t* hits);
+/* Raw device pointers of the accumulators (float4 image, float4-padded albedo / normal, int32
+ * hits) so that a host that owns a communicator (torch.distributed / NCCL) can reduce them in
+ * place across GPUs. `count` = width*height. */
+JT_API int jt_state_device_buffers(jt_state* state, void** image, void** albedo, void** normal,
+                                   void** hits, int64_t* count);
+/* After an external sum-reduction across ranks: set the number of samples the buffers hold. */
+JT_API int jt_state_set_samples(jt_state* state, int32_t samples);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* trace_samples (src/trace.jl:215-274): advances state.samples by params.batch (clamped to
+ * params.samples). Asynchronous: returns after enqueueing; nothing is copied back. */
+JT_API int jt_trace_samples(jt_scene* scene, jt_state* state, const jt_params* params);
+/* Same loop body for an explicit range of global sample indices [begin, end): the unit that
+ * is sharded across GPUs. Does not touch state.samples bookkeeping beyond adding end-begin. */
+JT_API int jt_trace_sample_range(jt_scene* scene, jt_state* state, const jt_params* params,
+                                 int32_t sample_begin, int32_t sample_end);
+/* Block until all enqueued work on this scene's stream is complete. */
+JT_API int jt_synchronize(jt_scene* scene);
+/* Device time in milliseconds spent by the render kernels enqueued since the last call
+ * (CUDA events on the library's stream); synchronises. */
+JT_API int jt_elapsed_ms(jt_scene* scene, float* ms);
+
+/* ---- parity hooks ("identical rays") -------------------------------------------------------- */
+/* intersect_scene_bvh (src/bvh.jl:306-371) for n host rays; find_any = false.
+ * traversal: 0 = wide BVH kernel, 1 = reference-order kernel. Results use 1-based ids. */
+JT_API int jt_intersect(jt_scene* scene, const jt_ray* rays, int64_t n, int traversal, jt_hit* out);
+/* intersect_instance_bvh (src/bvh.jl:493-520): one named instance (1-based) per ray. */
+JT_API int jt_intersect_instance(jt_scene* scene, const jt_ray* rays, const int64_t* instances,
+                                 int64_t n, int traversal, jt_hit* out);
+/* sample_camera + eval_camera (src/trace.jl:651-674, src/scene.jl:372-411) for explicit
+ * (i, j, puv, luv) tuples: rays out. */
+JT_API int jt_sample_camera(jt_scene* scene, const jt_params* params, int32_t width, int32_t height,
+                            const int32_t* ij, const float* puv_luv, int64_t n, jt_ray* out);
+/* Device-resident variant used by the benchmark: rays and hits are device pointers. */
+JT_API int jt_intersect_device(jt_scene* scene, const void* d_rays, int64_t n, int traversal,
+                               void* d_hits);
+
+/* ---- host-side helpers (CPU code; the steps bvh.jl performs on the Julia host) --------------- */
+/* make_bvh (src/bvh.jl:138-183) with split_middle (:185-216) or split_sah (:218-274):
+ * bboxes = n x {min[3], max[3]} floats. nodes_out must hold 2*n+1 entries, primitives_out n. */
+JT_API int jt_make_bvh(const float* bboxes, int64_t n, int high_quality, jt_bvh_node* nodes_out,
+                       int64_t* num_nodes_out, int64_t* primitives_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JTRACE_B200_H */
