@@ -1,0 +1,607 @@
+// jt_api.cu -- C ABI of libjtrace_b200.so (include/jtrace_b200.h): scene upload, device-resident
+// TraceState, the render-loop launches and the parity hooks. Kernels live at the bottom.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "jt_dev_trace.cuh"
+#include "jt_internal.h"
+
+// =================================================================================================
+// error channel
+// =================================================================================================
+static thread_local std::string g_error;
+
+int jt_set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define JT_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return jt_set_error(JT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+                          __LINE__);                                                                    \
+  } while (0)
+
+extern "C" const char* jt_last_error(void) { return g_error.c_str(); }
+extern "C" const char* jt_version(void) { return "jtrace_b200 0.1 (sm_100a)"; }
+extern "C" int jt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// =================================================================================================
+// scene
+// =================================================================================================
+struct jt_scene {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  bool timing_open = false;
+  std::vector<void*> allocs;
+  JtDevScene dev;
+  int num_cameras = 0, num_instances = 0;
+  unsigned long long* d_counters = nullptr;  // [0] camera paths [1] scene rays [2] light rays
+  uint64_t launches = 0;
+  jt_scene_stats stats;
+  int64_t device_bytes = 0;
+};
+
+struct jt_state {
+  jt_scene* scene = nullptr;
+  int width = 0, height = 0, samples = 0;
+  int accumulate = 0;
+  DevState dev;
+};
+
+template <class T>
+static int upload(jt_scene* sc, const std::vector<T>& v, const T** out) {
+  *out = nullptr;
+  size_t bytes = sizeof(T) * std::max<size_t>(v.size(), 1);
+  void* p = nullptr;
+  JT_CUDA(cudaMalloc(&p, bytes));
+  sc->allocs.push_back(p);
+  sc->device_bytes += (int64_t)bytes;
+  if (!v.empty()) JT_CUDA(cudaMemcpy(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  *out = (const T*)p;
+  return JT_OK;
+}
+
+extern "C" void jt_scene_destroy(jt_scene* sc) {
+  if (!sc) return;
+  cudaSetDevice(sc->device);
+  for (void* p : sc->allocs) cudaFree(p);
+  if (sc->ev_start) cudaEventDestroy(sc->ev_start);
+  if (sc->ev_stop) cudaEventDestroy(sc->ev_stop);
+  if (sc->stream) cudaStreamDestroy(sc->stream);
+  delete sc;
+}
+
+static int scene_create_impl(const jt_scene_desc* d, int device, jt_scene* sc) {
+  int ndev = jt_device_count();
+  if (ndev <= 0) return jt_set_error(JT_ERR_NO_DEVICE, "no CUDA device visible: libjtrace_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return jt_set_error(JT_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+  sc->device = device;
+  JT_CUDA(cudaSetDevice(device));
+  JT_CUDA(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
+  JT_CUDA(cudaEventCreate(&sc->ev_start));
+  JT_CUDA(cudaEventCreate(&sc->ev_stop));
+  memset(&sc->dev, 0, sizeof(sc->dev));
+  memset(&sc->stats, 0, sizeof(sc->stats));
+
+  JtStagedScene staged;
+  int rc = jt_stage_scene(d, &staged);
+  if (rc != JT_OK) return rc;
+  auto& wide = staged.wide;
+
+  // ---- upload -----------------------------------------------------------------------------------------------
+  JtDevScene& D = sc->dev;
+  JtStagedPointers P;
+  const JtWideNode* wn = nullptr;
+  const JtWideTri* wt = nullptr;
+  if ((rc = upload(sc, staged.ref_nodes, &P.ref_nodes)) || (rc = upload(sc, staged.ref_prims, &P.ref_prims)) ||
+      (rc = upload(sc, staged.shape_recs, &P.shapes)) || (rc = upload(sc, staged.positions, &P.positions)) ||
+      (rc = upload(sc, staged.normals, &P.normals)) || (rc = upload(sc, staged.texcoords, &P.texcoords)) ||
+      (rc = upload(sc, staged.colors, &P.colors)) || (rc = upload(sc, staged.elements, &P.elements)) ||
+      (rc = upload(sc, staged.inst_recs, &P.instances)) || (rc = upload(sc, staged.mats, &P.materials)) ||
+      (rc = upload(sc, staged.texs, &P.textures)) || (rc = upload(sc, staged.texels_f, &P.texels_f)) ||
+      (rc = upload(sc, staged.texels_b, &P.texels_b)) || (rc = upload(sc, staged.lut, &P.srgb_lut)) ||
+      (rc = upload(sc, staged.envs, &P.environments)) || (rc = upload(sc, staged.lights, &P.lights)) ||
+      (rc = upload(sc, staged.cdf, &P.light_cdf)) || (rc = upload(sc, staged.cams, &P.cameras)) ||
+      (rc = upload(sc, wide.nodes, &wn)) || (rc = upload(sc, wide.tris, &wt)) ||
+      (rc = upload(sc, staged.tri_rank, &P.tri_rank)) || (rc = upload(sc, staged.inst_rank, &P.inst_rank)))
+    return rc;
+  P.wnodes = (const float4*)wn;
+  P.wtris = (const float4*)wt;
+  jt_fill_dev_scene(staged, P, &D);
+  sc->num_cameras = (int)d->num_cameras;
+  sc->num_instances = (int)d->num_instances;
+  void* cnt = nullptr;
+  JT_CUDA(cudaMalloc(&cnt, 8 * sizeof(unsigned long long)));
+  sc->allocs.push_back(cnt);
+  JT_CUDA(cudaMemset(cnt, 0, 8 * sizeof(unsigned long long)));
+  sc->d_counters = (unsigned long long*)cnt;
+
+  sc->stats.wide_nodes = (int64_t)wide.nodes.size();
+  sc->stats.wide_node_bytes = (int64_t)wide.nodes.size() * 80;
+  sc->stats.prim_records = (int64_t)wide.tris.size();
+  sc->stats.prim_record_bytes = (int64_t)wide.tris.size() * 48;
+  sc->stats.inlined_instances = wide.inlined_instances;
+  sc->stats.instanced_instances = wide.instanced_instances;
+  sc->stats.texture_bytes = (int64_t)(staged.texels_f.size() * 16 + staged.texels_b.size() * 4);
+  sc->stats.total_device_bytes = sc->device_bytes;
+  sc->stats._reserved[0] = staged.depth;
+  sc->stats._reserved[1] = staged.blas_depth;
+  return JT_OK;
+}
+
+extern "C" int jt_scene_create(const jt_scene_desc* desc, int device, jt_scene** out) {
+  if (!desc || !out) return jt_set_error(JT_ERR_INVALID, "jt_scene_create: null argument");
+  *out = nullptr;
+  jt_scene* sc = new (std::nothrow) jt_scene();
+  if (!sc) return jt_set_error(JT_ERR_INTERNAL, "out of host memory");
+  int rc;
+  try {
+    rc = scene_create_impl(desc, device, sc);
+  } catch (const std::exception& e) {
+    rc = jt_set_error(JT_ERR_INTERNAL, "jt_scene_create: %s", e.what());
+  } catch (...) {
+    rc = jt_set_error(JT_ERR_INTERNAL, "jt_scene_create: unknown exception");
+  }
+  if (rc != JT_OK) {
+    std::string keep = g_error;
+    jt_scene_destroy(sc);
+    g_error = keep;
+    return rc;
+  }
+  *out = sc;
+  return JT_OK;
+}
+
+extern "C" int jt_scene_get_stats(jt_scene* sc, jt_scene_stats* out) {
+  if (!sc || !out) return jt_set_error(JT_ERR_INVALID, "jt_scene_get_stats: null argument");
+  *out = sc->stats;
+  return JT_OK;
+}
+
+extern "C" int jt_scene_counters(jt_scene* sc, jt_counters* out, int reset) {
+  if (!sc || !out) return jt_set_error(JT_ERR_INVALID, "jt_scene_counters: null argument");
+  JT_CUDA(cudaSetDevice(sc->device));
+  JT_CUDA(cudaStreamSynchronize(sc->stream));
+  unsigned long long h[8];
+  JT_CUDA(cudaMemcpy(h, sc->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+  memset(out, 0, sizeof(*out));
+  out->camera_paths = h[0];
+  out->scene_rays = h[1];
+  out->light_rays = h[2];
+  out->kernel_launches = sc->launches;
+  if (reset) {
+    JT_CUDA(cudaMemset(sc->d_counters, 0, sizeof(h)));
+    sc->launches = 0;
+  }
+  return JT_OK;
+}
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+struct HitOut {  // jt_hit
+  long long instance, element;
+  float u, v, distance;
+  unsigned int hit;
+};
+static_assert(sizeof(HitOut) == 32, "jt_hit layout");
+
+JT_DEV void store_hit(HitOut* out, const DHit& h) {
+  HitOut o;
+  if (h.inst >= 0) {
+    o.instance = h.inst + 1; o.element = h.elem + 1; o.u = h.u; o.v = h.v; o.distance = h.t; o.hit = 1u;
+  } else {
+    o.instance = -1; o.element = -1; o.u = 0.0f; o.v = 0.0f; o.distance = 0.0f; o.hit = 0u;
+  }
+  *out = o;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_intersect(JtDevScene S, const jt_ray* __restrict__ rays, long long n,
+                                                   HitOut* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  jt_ray r = rays[i];
+  DRay ray{f3{r.o[0], r.o[1], r.o[2]}, f3{r.d[0], r.d[1], r.d[2]}, r.tmin, r.tmax};
+  store_hit(out + i, intersect_scene<MODE>(S, ray));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_intersect_instance(JtDevScene S, const jt_ray* __restrict__ rays,
+                                                            const long long* __restrict__ instances, long long n,
+                                                            HitOut* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  jt_ray r = rays[i];
+  DRay ray{f3{r.o[0], r.o[1], r.o[2]}, f3{r.d[0], r.d[1], r.d[2]}, r.tmin, r.tmax};
+  int inst = (int)instances[i] - 1;
+  DHit h{0.0f, 0.0f, 0.0f, -1, -1};
+  if (inst >= 0 && inst < S.num_instances) h = intersect_instance<MODE>(S, inst, ray);
+  store_hit(out + i, h);
+}
+
+__global__ void k_sample_camera(JtDevScene S, int camera, int tent, int width, int height,
+                                const int* __restrict__ ij, const float* __restrict__ r, long long n, jt_ray* out) {
+  long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  DRay ray = sample_camera(S.cameras[camera], ij[2 * k], ij[2 * k + 1], width, height, f2{r[4 * k], r[4 * k + 1]},
+                           f2{r[4 * k + 2], r[4 * k + 3]}, tent != 0);
+  jt_ray o;
+  o.o[0] = ray.o.x; o.o[1] = ray.o.y; o.o[2] = ray.o.z;
+  o.d[0] = ray.d.x; o.d[1] = ray.d.y; o.d[2] = ray.d.z;
+  o.tmin = ray.tmin; o.tmax = ray.tmax;
+  out[k] = o;
+}
+
+// One thread per pixel, samples [begin, end) in order: the whole of trace_sample (src/trace.jl:584-649).
+// This "megakernel" form is the bit-exact parity integrator; warps cover 16x2 pixel tiles.
+template <int MODE>
+__global__ void __launch_bounds__(128) k_trace_mega(JtDevScene S, DevState st, DevParams P, int begin, int end,
+                                                    unsigned long long* counters) {
+  int i = blockIdx.x * 16 + (threadIdx.x & 15);
+  int j = blockIdx.y * 8 + (threadIdx.x >> 4);
+  PathCounters cnt{0u, 0u};
+  unsigned int paths = 0;
+  if (i < P.width && j < P.height) {
+    int idx = P.width * j + i;
+    const JtCameraRec& C = S.cameras[P.camera];
+    bool has_env = S.num_environments != 0;
+    for (int s = begin; s < end; s++) {
+      Rng rng{jt_rng_key(P.seed, (uint32_t)idx, (uint32_t)s), 0u};
+      f2 puv = rng.next2();
+      f2 luv = rng.next2();
+      DRay ray = sample_camera(C, i, j, P.width, P.height, puv, luv, P.tentfilter != 0);
+      TraceOut r = P.sampler == 1 ? trace_path<MODE>(S, ray, P, rng, cnt) : trace_naive<MODE>(S, ray, P, rng, cnt);
+      accumulate_sample(st, P, has_env, idx, s, r, ray.d);
+      paths++;
+    }
+  }
+  // one atomic per warp per counter
+  unsigned int a = __reduce_add_sync(0xFFFFFFFFu, paths);
+  unsigned int b = __reduce_add_sync(0xFFFFFFFFu, cnt.scene_rays);
+  unsigned int c = __reduce_add_sync(0xFFFFFFFFu, cnt.light_rays);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(counters + 0, (unsigned long long)a);
+    atomicAdd(counters + 1, (unsigned long long)b);
+    atomicAdd(counters + 2, (unsigned long long)c);
+  }
+}
+
+__global__ void k_finalize(const float4* __restrict__ image, const float4* __restrict__ albedo,
+                           const float4* __restrict__ normal, const int* __restrict__ hits, long long n, float scale,
+                           float* out_image, float* out_albedo, float* out_normal, long long* out_hits) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = image[i], b = albedo[i], c = normal[i];
+  if (out_image) {
+    out_image[4 * i] = a.x * scale; out_image[4 * i + 1] = a.y * scale; out_image[4 * i + 2] = a.z * scale;
+    out_image[4 * i + 3] = a.w * scale;
+  }
+  if (out_albedo) {
+    out_albedo[3 * i] = b.x * scale; out_albedo[3 * i + 1] = b.y * scale; out_albedo[3 * i + 2] = b.z * scale;
+  }
+  if (out_normal) {
+    out_normal[3 * i] = c.x * scale; out_normal[3 * i + 1] = c.y * scale; out_normal[3 * i + 2] = c.z * scale;
+  }
+  if (out_hits) out_hits[i] = hits[i];
+}
+
+// =================================================================================================
+// state
+// =================================================================================================
+static int check_params(jt_scene* sc, const jt_params* p) {
+  if (!p) return jt_set_error(JT_ERR_INVALID, "null params");
+  if (p->camera < 1 || p->camera > sc->num_cameras) return jt_set_error(JT_ERR_INVALID, "camera %d out of range (1..%d)", p->camera, sc->num_cameras);
+  if (p->sampler != 1 && p->sampler != 2) return jt_set_error(JT_ERR_INVALID, "sampler must be 1 (path) or 2 (naive)");
+  if (p->resolution < 1 || p->resolution > 32768) return jt_set_error(JT_ERR_INVALID, "bad resolution %d", p->resolution);
+  if (p->traversal != 0 && p->traversal != 1) return jt_set_error(JT_ERR_INVALID, "traversal must be 0 (wide) or 1 (reference)");
+  if (p->accumulate != 0 && p->accumulate != 1) return jt_set_error(JT_ERR_INVALID, "accumulate must be 0 or 1");
+  if (p->sampler == 1 && sc->dev.num_lights == 0)
+    return jt_set_error(JT_ERR_UNSUPPORTED, "path sampler on a scene without lights: sample_lights indexes an empty array in the reference");
+  return JT_OK;
+}
+
+extern "C" int jt_state_create(jt_scene* sc, const jt_params* p, jt_state** out) {
+  if (!sc || !out) return jt_set_error(JT_ERR_INVALID, "jt_state_create: null argument");
+  *out = nullptr;
+  int rc = check_params(sc, p);
+  if (rc) return rc;
+  JT_CUDA(cudaSetDevice(sc->device));
+  JtCameraRec cam;
+  JT_CUDA(cudaMemcpy(&cam, sc->dev.cameras + (p->camera - 1), sizeof(cam), cudaMemcpyDeviceToHost));
+  int w, h;  // make_trace_state, src/trace.jl:189-197 (Float32 division, round half to even)
+  if (cam.aspect >= 1.0f) {
+    w = p->resolution;
+    h = (int)nearbyintf((float)p->resolution / cam.aspect);
+  } else {
+    h = p->resolution;
+    w = (int)nearbyintf((float)p->resolution * cam.aspect);
+  }
+  if (w < 1 || h < 1) return jt_set_error(JT_ERR_INVALID, "degenerate image size %dx%d", w, h);
+  jt_state* st = new (std::nothrow) jt_state();
+  if (!st) return jt_set_error(JT_ERR_INTERNAL, "out of host memory");
+  st->scene = sc;
+  st->width = w;
+  st->height = h;
+  st->accumulate = p->accumulate;
+  size_t n = (size_t)w * h;
+  void *a = nullptr, *b = nullptr, *c = nullptr, *d = nullptr;
+  if (cudaMalloc(&a, n * 16) != cudaSuccess || cudaMalloc(&b, n * 16) != cudaSuccess ||
+      cudaMalloc(&c, n * 16) != cudaSuccess || cudaMalloc(&d, n * 4) != cudaSuccess) {
+    cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d);
+    delete st;
+    return jt_set_error(JT_ERR_CUDA, "cudaMalloc of the trace state failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  st->dev.image = (float4*)a; st->dev.albedo = (float4*)b; st->dev.normal = (float4*)c; st->dev.hits = (int*)d;
+  *out = st;
+  return jt_state_reset(st);
+}
+
+extern "C" int jt_state_reset(jt_state* st) {
+  if (!st) return jt_set_error(JT_ERR_INVALID, "jt_state_reset: null argument");
+  jt_scene* sc = st->scene;
+  JT_CUDA(cudaSetDevice(sc->device));
+  size_t n = (size_t)st->width * st->height;
+  JT_CUDA(cudaMemsetAsync(st->dev.image, 0, n * 16, sc->stream));
+  JT_CUDA(cudaMemsetAsync(st->dev.albedo, 0, n * 16, sc->stream));
+  JT_CUDA(cudaMemsetAsync(st->dev.normal, 0, n * 16, sc->stream));
+  JT_CUDA(cudaMemsetAsync(st->dev.hits, 0, n * 4, sc->stream));
+  st->samples = 0;
+  return JT_OK;
+}
+
+extern "C" void jt_state_destroy(jt_state* st) {
+  if (!st) return;
+  cudaSetDevice(st->scene->device);
+  cudaStreamSynchronize(st->scene->stream);
+  cudaFree(st->dev.image); cudaFree(st->dev.albedo); cudaFree(st->dev.normal); cudaFree(st->dev.hits);
+  delete st;
+}
+
+extern "C" int jt_state_size(jt_state* st, int32_t* width, int32_t* height, int32_t* samples) {
+  if (!st) return jt_set_error(JT_ERR_INVALID, "jt_state_size: null argument");
+  if (width) *width = st->width;
+  if (height) *height = st->height;
+  if (samples) *samples = st->samples;
+  return JT_OK;
+}
+
+extern "C" int jt_state_set_samples(jt_state* st, int32_t samples) {
+  if (!st || samples < 0) return jt_set_error(JT_ERR_INVALID, "jt_state_set_samples: bad argument");
+  st->samples = samples;
+  return JT_OK;
+}
+
+extern "C" int jt_state_device_buffers(jt_state* st, void** image, void** albedo, void** normal, void** hits,
+                                       int64_t* count) {
+  if (!st) return jt_set_error(JT_ERR_INVALID, "jt_state_device_buffers: null argument");
+  if (image) *image = st->dev.image;
+  if (albedo) *albedo = st->dev.albedo;
+  if (normal) *normal = st->dev.normal;
+  if (hits) *hits = st->dev.hits;
+  if (count) *count = (int64_t)st->width * st->height;
+  return JT_OK;
+}
+
+extern "C" int jt_state_download(jt_state* st, float* image, float* albedo, float* normal, int64_t* hits) {
+  if (!st) return jt_set_error(JT_ERR_INVALID, "jt_state_download: null argument");
+  jt_scene* sc = st->scene;
+  JT_CUDA(cudaSetDevice(sc->device));
+  long long n = (long long)st->width * st->height;
+  float *di = nullptr, *da = nullptr, *dn = nullptr;
+  long long* dh = nullptr;
+  int rc = JT_OK;
+  auto fail = [&](cudaError_t e) { rc = jt_set_error(JT_ERR_CUDA, "jt_state_download: %s", cudaGetErrorString(e)); };
+  cudaError_t e;
+  if (image && (e = cudaMalloc((void**)&di, n * 16)) != cudaSuccess) fail(e);
+  if (!rc && albedo && (e = cudaMalloc((void**)&da, n * 12)) != cudaSuccess) fail(e);
+  if (!rc && normal && (e = cudaMalloc((void**)&dn, n * 12)) != cudaSuccess) fail(e);
+  if (!rc && hits && (e = cudaMalloc((void**)&dh, n * 8)) != cudaSuccess) fail(e);
+  if (!rc) {
+    float scale = (st->accumulate == 1 && st->samples > 0) ? 1.0f / (float)st->samples : 1.0f;
+    k_finalize<<<(unsigned)((n + 255) / 256), 256, 0, sc->stream>>>(st->dev.image, st->dev.albedo, st->dev.normal,
+                                                                     st->dev.hits, n, scale, di, da, dn, dh);
+    sc->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) fail(e);
+    if (!rc && image && (e = cudaMemcpyAsync(image, di, n * 16, cudaMemcpyDeviceToHost, sc->stream)) != cudaSuccess) fail(e);
+    if (!rc && albedo && (e = cudaMemcpyAsync(albedo, da, n * 12, cudaMemcpyDeviceToHost, sc->stream)) != cudaSuccess) fail(e);
+    if (!rc && normal && (e = cudaMemcpyAsync(normal, dn, n * 12, cudaMemcpyDeviceToHost, sc->stream)) != cudaSuccess) fail(e);
+    if (!rc && hits && (e = cudaMemcpyAsync(hits, dh, n * 8, cudaMemcpyDeviceToHost, sc->stream)) != cudaSuccess) fail(e);
+    if ((e = cudaStreamSynchronize(sc->stream)) != cudaSuccess && !rc) fail(e);
+  }
+  cudaFree(di); cudaFree(da); cudaFree(dn); cudaFree(dh);
+  return rc;
+}
+
+// =================================================================================================
+// the hot path
+// =================================================================================================
+static DevParams dev_params(const jt_params* p, const jt_state* st) {
+  DevParams P;
+  P.camera = p->camera - 1;
+  P.width = st->width; P.height = st->height;
+  P.bounces = p->bounces; P.sampler = p->sampler; P.clamp = p->clamp;
+  P.nocaustics = p->nocaustics; P.envhidden = p->envhidden; P.tentfilter = p->tentfilter;
+  P.accumulate = st->accumulate;
+  P.seed = p->seed;
+  return P;
+}
+
+static int launch_range(jt_scene* sc, jt_state* st, const jt_params* p, int begin, int end) {
+  if (end <= begin) return JT_OK;
+  DevParams P = dev_params(p, st);
+  dim3 grid((unsigned)((st->width + 15) / 16), (unsigned)((st->height + 7) / 8));
+  if (!sc->timing_open) {
+    JT_CUDA(cudaEventRecord(sc->ev_start, sc->stream));
+    sc->timing_open = true;
+  }
+  if (p->traversal == 1) k_trace_mega<MODE_REF><<<grid, 128, 0, sc->stream>>>(sc->dev, st->dev, P, begin, end, sc->d_counters);
+  else k_trace_mega<MODE_WIDE><<<grid, 128, 0, sc->stream>>>(sc->dev, st->dev, P, begin, end, sc->d_counters);
+  sc->launches++;
+  JT_CUDA(cudaGetLastError());
+  JT_CUDA(cudaEventRecord(sc->ev_stop, sc->stream));
+  return JT_OK;
+}
+
+extern "C" int jt_trace_sample_range(jt_scene* sc, jt_state* st, const jt_params* p, int32_t begin, int32_t end) {
+  if (!sc || !st || st->scene != sc) return jt_set_error(JT_ERR_INVALID, "jt_trace_sample_range: bad scene/state");
+  int rc = check_params(sc, p);
+  if (rc) return rc;
+  if (begin < 0 || end < begin) return jt_set_error(JT_ERR_INVALID, "bad sample range [%d, %d)", begin, end);
+  JT_CUDA(cudaSetDevice(sc->device));
+  rc = launch_range(sc, st, p, begin, end);
+  if (rc) return rc;
+  st->samples += end - begin;
+  return JT_OK;
+}
+
+extern "C" int jt_trace_samples(jt_scene* sc, jt_state* st, const jt_params* p) {
+  if (!sc || !st || st->scene != sc) return jt_set_error(JT_ERR_INVALID, "jt_trace_samples: bad scene/state");
+  int rc = check_params(sc, p);
+  if (rc) return rc;
+  if (st->samples >= p->samples) return JT_OK;  // src/trace.jl:225-227
+  int target = std::min(st->samples + std::max(p->batch, 1), p->samples);
+  return jt_trace_sample_range(sc, st, p, st->samples, target);
+}
+
+extern "C" int jt_synchronize(jt_scene* sc) {
+  if (!sc) return jt_set_error(JT_ERR_INVALID, "jt_synchronize: null argument");
+  JT_CUDA(cudaSetDevice(sc->device));
+  JT_CUDA(cudaStreamSynchronize(sc->stream));
+  return JT_OK;
+}
+
+extern "C" int jt_elapsed_ms(jt_scene* sc, float* ms) {
+  if (!sc || !ms) return jt_set_error(JT_ERR_INVALID, "jt_elapsed_ms: null argument");
+  JT_CUDA(cudaSetDevice(sc->device));
+  *ms = 0.0f;
+  if (!sc->timing_open) return JT_OK;
+  JT_CUDA(cudaEventSynchronize(sc->ev_stop));
+  JT_CUDA(cudaEventElapsedTime(ms, sc->ev_start, sc->ev_stop));
+  sc->timing_open = false;
+  return JT_OK;
+}
+
+// =================================================================================================
+// parity hooks
+// =================================================================================================
+extern "C" int jt_intersect_device(jt_scene* sc, const void* d_rays, int64_t n, int traversal, void* d_hits) {
+  if (!sc || (n > 0 && (!d_rays || !d_hits)) || n < 0) return jt_set_error(JT_ERR_INVALID, "jt_intersect_device: bad argument");
+  if (traversal != 0 && traversal != 1) return jt_set_error(JT_ERR_INVALID, "traversal must be 0 or 1");
+  if (n == 0) return JT_OK;
+  JT_CUDA(cudaSetDevice(sc->device));
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  if (!sc->timing_open) {
+    JT_CUDA(cudaEventRecord(sc->ev_start, sc->stream));
+    sc->timing_open = true;
+  }
+  if (traversal == 1) k_intersect<MODE_REF><<<blocks, 128, 0, sc->stream>>>(sc->dev, (const jt_ray*)d_rays, n, (HitOut*)d_hits);
+  else k_intersect<MODE_WIDE><<<blocks, 128, 0, sc->stream>>>(sc->dev, (const jt_ray*)d_rays, n, (HitOut*)d_hits);
+  sc->launches++;
+  JT_CUDA(cudaGetLastError());
+  JT_CUDA(cudaEventRecord(sc->ev_stop, sc->stream));
+  return JT_OK;
+}
+
+extern "C" int jt_intersect(jt_scene* sc, const jt_ray* rays, int64_t n, int traversal, jt_hit* out) {
+  if (!sc || (n > 0 && (!rays || !out)) || n < 0) return jt_set_error(JT_ERR_INVALID, "jt_intersect: bad argument");
+  if (n == 0) return JT_OK;
+  JT_CUDA(cudaSetDevice(sc->device));
+  void *dr = nullptr, *dh = nullptr;
+  JT_CUDA(cudaMalloc(&dr, n * sizeof(jt_ray)));
+  cudaError_t e = cudaMalloc(&dh, n * sizeof(jt_hit));
+  if (e != cudaSuccess) {
+    cudaFree(dr);
+    return jt_set_error(JT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  int rc = JT_OK;
+  if ((e = cudaMemcpyAsync(dr, rays, n * sizeof(jt_ray), cudaMemcpyHostToDevice, sc->stream)) != cudaSuccess)
+    rc = jt_set_error(JT_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  if (!rc) rc = jt_intersect_device(sc, dr, n, traversal, dh);
+  if (!rc && (e = cudaMemcpyAsync(out, dh, n * sizeof(jt_hit), cudaMemcpyDeviceToHost, sc->stream)) != cudaSuccess)
+    rc = jt_set_error(JT_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+  if ((e = cudaStreamSynchronize(sc->stream)) != cudaSuccess && !rc)
+    rc = jt_set_error(JT_ERR_CUDA, "jt_intersect: %s", cudaGetErrorString(e));
+  cudaFree(dr);
+  cudaFree(dh);
+  return rc;
+}
+
+extern "C" int jt_intersect_instance(jt_scene* sc, const jt_ray* rays, const int64_t* instances, int64_t n,
+                                     int traversal, jt_hit* out) {
+  if (!sc || (n > 0 && (!rays || !out || !instances)) || n < 0) return jt_set_error(JT_ERR_INVALID, "jt_intersect_instance: bad argument");
+  if (traversal != 0 && traversal != 1) return jt_set_error(JT_ERR_INVALID, "traversal must be 0 or 1");
+  if (n == 0) return JT_OK;
+  JT_CUDA(cudaSetDevice(sc->device));
+  void *dr = nullptr, *dh = nullptr, *di = nullptr;
+  cudaError_t e;
+  int rc = JT_OK;
+  if ((e = cudaMalloc(&dr, n * sizeof(jt_ray))) != cudaSuccess || (e = cudaMalloc(&dh, n * sizeof(jt_hit))) != cudaSuccess ||
+      (e = cudaMalloc(&di, n * 8)) != cudaSuccess)
+    rc = jt_set_error(JT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  if (!rc && ((e = cudaMemcpyAsync(dr, rays, n * sizeof(jt_ray), cudaMemcpyHostToDevice, sc->stream)) != cudaSuccess ||
+              (e = cudaMemcpyAsync(di, instances, n * 8, cudaMemcpyHostToDevice, sc->stream)) != cudaSuccess))
+    rc = jt_set_error(JT_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  if (!rc) {
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (traversal == 1) k_intersect_instance<MODE_REF><<<blocks, 128, 0, sc->stream>>>(sc->dev, (const jt_ray*)dr, (const long long*)di, n, (HitOut*)dh);
+    else k_intersect_instance<MODE_WIDE><<<blocks, 128, 0, sc->stream>>>(sc->dev, (const jt_ray*)dr, (const long long*)di, n, (HitOut*)dh);
+    sc->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) rc = jt_set_error(JT_ERR_CUDA, "launch failed: %s", cudaGetErrorString(e));
+  }
+  if (!rc && (e = cudaMemcpyAsync(out, dh, n * sizeof(jt_hit), cudaMemcpyDeviceToHost, sc->stream)) != cudaSuccess)
+    rc = jt_set_error(JT_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+  if ((e = cudaStreamSynchronize(sc->stream)) != cudaSuccess && !rc) rc = jt_set_error(JT_ERR_CUDA, "jt_intersect_instance: %s", cudaGetErrorString(e));
+  cudaFree(dr); cudaFree(dh); cudaFree(di);
+  return rc;
+}
+
+extern "C" int jt_sample_camera(jt_scene* sc, const jt_params* p, int32_t width, int32_t height, const int32_t* ij,
+                                const float* puv_luv, int64_t n, jt_ray* out) {
+  if (!sc || !p || (n > 0 && (!ij || !puv_luv || !out)) || n < 0) return jt_set_error(JT_ERR_INVALID, "jt_sample_camera: bad argument");
+  if (p->camera < 1 || p->camera > sc->num_cameras) return jt_set_error(JT_ERR_INVALID, "camera out of range");
+  if (n == 0) return JT_OK;
+  JT_CUDA(cudaSetDevice(sc->device));
+  void *dij = nullptr, *dr = nullptr, *dout = nullptr;
+  cudaError_t e;
+  int rc = JT_OK;
+  if ((e = cudaMalloc(&dij, n * 8)) != cudaSuccess || (e = cudaMalloc(&dr, n * 16)) != cudaSuccess ||
+      (e = cudaMalloc(&dout, n * sizeof(jt_ray))) != cudaSuccess)
+    rc = jt_set_error(JT_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  if (!rc && ((e = cudaMemcpyAsync(dij, ij, n * 8, cudaMemcpyHostToDevice, sc->stream)) != cudaSuccess ||
+              (e = cudaMemcpyAsync(dr, puv_luv, n * 16, cudaMemcpyHostToDevice, sc->stream)) != cudaSuccess))
+    rc = jt_set_error(JT_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+  if (!rc) {
+    k_sample_camera<<<(unsigned)((n + 127) / 128), 128, 0, sc->stream>>>(sc->dev, p->camera - 1, p->tentfilter, width, height,
+                                                                         (const int*)dij, (const float*)dr, n, (jt_ray*)dout);
+    sc->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) rc = jt_set_error(JT_ERR_CUDA, "launch failed: %s", cudaGetErrorString(e));
+  }
+  if (!rc && (e = cudaMemcpyAsync(out, dout, n * sizeof(jt_ray), cudaMemcpyDeviceToHost, sc->stream)) != cudaSuccess)
+    rc = jt_set_error(JT_ERR_CUDA, "D2H copy failed: %s", cudaGetErrorString(e));
+  if ((e = cudaStreamSynchronize(sc->stream)) != cudaSuccess && !rc) rc = jt_set_error(JT_ERR_CUDA, "jt_sample_camera: %s", cudaGetErrorString(e));
+  cudaFree(dij); cudaFree(dr); cudaFree(dout);
+  return rc;
+}

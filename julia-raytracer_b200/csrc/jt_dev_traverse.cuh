@@ -1,0 +1,385 @@
+// jt_dev_traverse.cuh -- closest-hit queries.
+//
+// Replaces intersect_scene_bvh (src/bvh.jl:306-371), intersect_shape_bvh (:373-491) and
+// intersect_instance_bvh (:493-520), with intersect_bbox / intersect_triangle / intersect_quad
+// (src/geometry.jl:96-105, :206-258) as leaf and node tests.
+//
+// Two implementations behind one interface (template parameter MODE):
+//   MODE_REF  -- the host-built binary BVH walked in the reference's own order (far child first,
+//                Q1), `t <= tmax` acceptance with overwrite (Q2), Float64 slab fudge (Q3),
+//                NaN-propagating min/max (Q4). Bit-exact by construction; it is the parity mode.
+//   MODE_WIDE -- the 8-wide quantised BVH of jt_wide_bvh.cpp: octant-ordered near-first descent,
+//                128-bit node/triangle fetches, one traversal for both levels (instance records
+//                switch the ray into instance space and back). The leaf test is the same exact
+//                arithmetic; exact-t ties fall back to the reference's visit-rank tables.
+#pragma once
+#include "jt_dev_math.cuh"
+
+enum { MODE_WIDE = 0, MODE_REF = 1 };
+
+// ---- exact leaf test --------------------------------------------------------------------------
+// intersect_triangle (src/geometry.jl:206-236) on a record that stores p1, p2-p1, p3-p1.
+// Returns true and (t,u,v) when the reference's test accepts against [tmin, tmax].
+JT_DEV bool tri_test(f3 o, f3 d, float tmin, float tmax, f3 p1, f3 edge1, f3 edge2, float* t, float* u,
+                     float* v) {
+  f3 pvec = cross3(d, edge2);
+  float det = dot3(edge1, pvec);
+  if (det == 0.0f) return false;
+  float inv_det = 1.0f / det;
+  f3 tvec = o - p1;
+  float uu = dot3(tvec, pvec) * inv_det;
+  if (uu < 0.0f || uu > 1.0f) return false;
+  f3 qvec = cross3(tvec, edge1);
+  float vv = dot3(d, qvec) * inv_det;
+  if (vv < 0.0f || uu + vv > 1.0f) return false;
+  float tt = dot3(edge2, qvec) * inv_det;
+  if (tt < tmin || tt > tmax) return false;
+  *t = tt;
+  *u = uu;
+  *v = vv;
+  return true;
+}
+
+// ===============================================================================================
+// MODE_REF
+// ===============================================================================================
+#define JT_REF_STACK 128 /* the reference's default --bvhstacksize (src/cli.jl:82-85) */
+
+// intersect_bbox, src/geometry.jl:96-105
+JT_DEV bool ref_bbox(f3 o, f3 dinv, float tmin, float tmax, f3 bmin, f3 bmax) {
+  f3 it_min = (bmin - o) * dinv;
+  f3 it_max = (bmax - o) * dinv;
+  float lo = jl_max(jl_max(jl_min(it_min.x, it_max.x), jl_min(it_min.y, it_max.y)), jl_min(it_min.z, it_max.z));
+  float hi = jl_min(jl_min(jl_max(it_min.x, it_max.x), jl_max(it_min.y, it_max.y)), jl_max(it_min.z, it_max.z));
+  float t0 = jl_max(lo, tmin);
+  float t1 = jl_min(hi, tmax);
+  double t1d = (double)t1 * 1.00000024;  // Q3
+  return (double)t0 <= t1d;
+}
+
+// intersect_shape_bvh on one shape, ray already in instance space. Updates best (t,u,v,elem).
+JT_DEV bool ref_shape(const JtDevScene& S, const JtShapeRec& sh, f3 o, f3 d, float tmin, float tmax, float* bt,
+                      float* bu, float* bv, int* belem) {
+  if (sh.num_ref_nodes == 0) return false;
+  int stack[JT_REF_STACK];
+  int sp = 0;
+  stack[sp++] = 0;
+  bool hit = false;
+  f3 dinv = f3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+  const float4* nodes = S.ref_nodes + 2 * (size_t)sh.ref_node_off;
+  const int32_t* prims = S.ref_prims + sh.ref_prim_off;
+  const float* pos = S.positions + 3 * (size_t)sh.pos_off;
+  const int4* elems = S.elements + sh.elem_off;
+  while (sp != 0) {
+    int ni = stack[--sp];
+    float4 a = __ldg(nodes + 2 * ni), b = __ldg(nodes + 2 * ni + 1);
+    if (!ref_bbox(o, dinv, tmin, tmax, f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y})) continue;
+    int start = __float_as_int(b.z);
+    int packed = __float_as_int(b.w);
+    int num = packed & 0xFFFF, axis = (packed >> 16) & 0xFF, internal = packed >> 24;
+    if (internal) {
+      float da = axis == 0 ? d.x : (axis == 1 ? d.y : d.z);
+      if (!(da < 0.0f)) {  // ray_dsign == 0: push start, start+1 -> start+1 popped first (Q1)
+        stack[sp++] = start;
+        stack[sp++] = start + 1;
+      } else {
+        stack[sp++] = start + 1;
+        stack[sp++] = start;
+      }
+    } else {
+      for (int i = start; i < start + num; i++) {
+        int e = __ldg(prims + i);
+        int4 q = __ldg(elems + e);
+        f3 p1 = ld3(pos + 3 * q.x), p2 = ld3(pos + 3 * q.y);
+        float t, u, v;
+        if (sh.kind == 1) {
+          f3 p3 = ld3(pos + 3 * q.z);
+          if (!tri_test(o, d, tmin, tmax, p1, p2 - p1, p3 - p1, &t, &u, &v)) continue;
+        } else {
+          // intersect_quad, src/geometry.jl:238-258
+          f3 p3 = ld3(pos + 3 * q.z), p4 = ld3(pos + 3 * q.w);
+          float t1 = 0, u1 = 0, v1 = 0, t2 = 0, u2 = 0, v2 = 0;
+          bool h1 = tri_test(o, d, tmin, tmax, p1, p2 - p1, p4 - p1, &t1, &u1, &v1);
+          if (p3 == p4) {
+            if (!h1) continue;
+            t = t1; u = u1; v = v1;
+          } else {
+            bool h2 = tri_test(o, d, tmin, tmax, p3, p4 - p3, p2 - p3, &t2, &u2, &v2);
+            // isec1.distance < isec2.distance ? isec1 : isec2, misses carry distance = +Inf
+            float d1 = h1 ? t1 : INFINITY, d2 = h2 ? t2 : INFINITY;
+            if (d1 < d2) {
+              t = t1; u = u1; v = v1;
+            } else {
+              if (!h2) continue;
+              t = t2; u = 1.0f - u2; v = 1.0f - v2;
+            }
+          }
+        }
+        *bt = t; *bu = u; *bv = v; *belem = e;  // Q2: every accepted hit overwrites
+        tmax = t;
+        hit = true;
+      }
+    }
+  }
+  return hit;
+}
+
+// intersect_instance_bvh
+JT_DEV DHit ref_instance(const JtDevScene& S, int inst, const DRay& ray) {
+  const JtInstanceRec& I = S.instances[inst];
+  f3 o = xform_point(I.inv, ray.o), d = xform_vector(I.inv, ray.d);
+  DHit h{0.0f, 0.0f, 0.0f, -1, -1};
+  float t, u, v;
+  int e;
+  if (ref_shape(S, S.shapes[I.shape], o, d, ray.tmin, ray.tmax, &t, &u, &v, &e)) h = DHit{t, u, v, inst, e};
+  return h;
+}
+
+// intersect_scene_bvh
+JT_DEV DHit ref_scene(const JtDevScene& S, const DRay& ray) {
+  DHit best{0.0f, 0.0f, 0.0f, -1, -1};
+  if (S.tlas_num_nodes == 0) return best;
+  int stack[JT_REF_STACK];
+  int sp = 0;
+  stack[sp++] = 0;
+  f3 o = ray.o, d = ray.d;
+  float tmax = ray.tmax;
+  f3 dinv = f3{1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
+  while (sp != 0) {
+    int ni = stack[--sp];
+    float4 a = __ldg(S.ref_nodes + 2 * ni), b = __ldg(S.ref_nodes + 2 * ni + 1);
+    if (!ref_bbox(o, dinv, ray.tmin, tmax, f3{a.x, a.y, a.z}, f3{a.w, b.x, b.y})) continue;
+    int start = __float_as_int(b.z);
+    int packed = __float_as_int(b.w);
+    int num = packed & 0xFFFF, axis = (packed >> 16) & 0xFF, internal = packed >> 24;
+    if (internal) {
+      float da = axis == 0 ? d.x : (axis == 1 ? d.y : d.z);
+      if (!(da < 0.0f)) {
+        stack[sp++] = start;
+        stack[sp++] = start + 1;
+      } else {
+        stack[sp++] = start + 1;
+        stack[sp++] = start;
+      }
+    } else {
+      for (int i = start; i < start + num; i++) {
+        int inst = __ldg(S.ref_prims + i);
+        const JtInstanceRec& I = S.instances[inst];
+        f3 io = xform_point(I.inv, o), id = xform_vector(I.inv, d);
+        float t, u, v;
+        int e;
+        if (!ref_shape(S, S.shapes[I.shape], io, id, ray.tmin, tmax, &t, &u, &v, &e)) continue;
+        best = DHit{t, u, v, inst, e};
+        tmax = t;
+      }
+    }
+  }
+  return best;
+}
+
+// ===============================================================================================
+// MODE_WIDE
+// ===============================================================================================
+#define JT_WIDE_STACK 40
+
+struct WideRay {  // per-space traversal constants
+  f3 o, d;
+  float idx, idy, idz;  // guarded reciprocal direction for the slab tests
+  uint32_t oct;         // slot index pointing along the ray: bit k set <=> d[k] >= 0
+  uint32_t rank_oct;    // reference octant: bit k set <=> d[k] < 0
+};
+
+JT_DEV float guarded_rcp(float d) {
+  const float tiny = 1e-30f;
+  float a = fabsf(d) < tiny ? copysignf(tiny, d) : d;
+  return 1.0f / a;
+}
+JT_DEV void wide_ray_setup(WideRay& R, f3 o, f3 d) {
+  R.o = o;
+  R.d = d;
+  R.idx = guarded_rcp(d.x);
+  R.idy = guarded_rcp(d.y);
+  R.idz = guarded_rcp(d.z);
+  uint32_t neg = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+  R.rank_oct = neg;
+  R.oct = neg ^ 7u;
+}
+
+JT_DEV uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
+
+// Slab-test the 8 children of one node. Returns the 32-bit hit word: bits 24..31 internal
+// children in priority order, bits 0..23 triangle records.
+JT_DEV uint32_t wide_node_hits(const float4* __restrict__ wnodes, uint32_t node, const WideRay& R, float tmin,
+                               float tmax, uint2* ngroup_out, uint2* tgroup_out) {
+  const float4* np = wnodes + 5 * (size_t)node;
+  float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+  uint32_t eimask = __float_as_uint(n0.w);
+  // grid step scaled by the reciprocal direction; origin term; absolute slack covering the
+  // rounding of this (fused) formulation so the test never rejects what exact arithmetic accepts
+  float sx = __uint_as_float((eimask & 0xFFu) << 23) * R.idx;
+  float sy = __uint_as_float(((eimask >> 8) & 0xFFu) << 23) * R.idy;
+  float sz = __uint_as_float(((eimask >> 16) & 0xFFu) << 23) * R.idz;
+  float ax = (n0.x - R.o.x) * R.idx, ay = (n0.y - R.o.y) * R.idy, az = (n0.z - R.o.z) * R.idz;
+  const float k = 4.76837158e-7f;  // 2^-21
+  float ex = k * fmaf(256.0f, fabsf(sx), fabsf(ax));
+  float ey = k * fmaf(256.0f, fabsf(sy), fabsf(ay));
+  float ez = k * fmaf(256.0f, fabsf(sz), fabsf(az));
+  float alx = ax - ex, ahx = ax + ex, aly = ay - ey, ahy = ay + ey, alz = az - ez, ahz = az + ez;
+  uint32_t imask = eimask >> 24;
+  uint32_t meta_w[2] = {__float_as_uint(n1.z), __float_as_uint(n1.w)};
+  uint32_t qlox[2] = {__float_as_uint(n2.x), __float_as_uint(n2.y)};
+  uint32_t qloy[2] = {__float_as_uint(n2.z), __float_as_uint(n2.w)};
+  uint32_t qloz[2] = {__float_as_uint(n3.x), __float_as_uint(n3.y)};
+  uint32_t qhix[2] = {__float_as_uint(n3.z), __float_as_uint(n3.w)};
+  uint32_t qhiy[2] = {__float_as_uint(n4.x), __float_as_uint(n4.y)};
+  uint32_t qhiz[2] = {__float_as_uint(n4.z), __float_as_uint(n4.w)};
+  const bool px = R.d.x >= 0.0f, py = R.d.y >= 0.0f, pz = R.d.z >= 0.0f;
+  uint32_t hits = 0;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint32_t nearx = px ? qlox[h] : qhix[h], farx = px ? qhix[h] : qlox[h];
+    uint32_t neary = py ? qloy[h] : qhiy[h], fary = py ? qhiy[h] : qloy[h];
+    uint32_t nearz = pz ? qloz[h] : qhiz[h], farz = pz ? qhiz[h] : qloz[h];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      uint32_t meta = byte_of(meta_w[h], j);
+      float t0x = fmaf((float)byte_of(nearx, j), sx, alx), t1x = fmaf((float)byte_of(farx, j), sx, ahx);
+      float t0y = fmaf((float)byte_of(neary, j), sy, aly), t1y = fmaf((float)byte_of(fary, j), sy, ahy);
+      float t0z = fmaf((float)byte_of(nearz, j), sz, alz), t1z = fmaf((float)byte_of(farz, j), sz, ahz);
+      float lo = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
+      float hi = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
+      if (meta != 0u && lo <= hi) {
+        bool inner = (meta & 0x18u) == 0x18u;
+        uint32_t bit_index = inner ? (24u + ((meta & 7u) ^ R.oct)) : (meta & 31u);
+        uint32_t child_bits = inner ? 1u : (meta >> 5);
+        hits |= child_bits << bit_index;
+      }
+    }
+  }
+  *ngroup_out = make_uint2(__float_as_uint(n1.x), (hits & 0xFF000000u) | imask);
+  *tgroup_out = make_uint2(__float_as_uint(n1.y), hits & 0x00FFFFFFu);
+  return hits;
+}
+
+struct WideBest {
+  float t, u, v;
+  int inst, elem;
+  int wtri;  // record index of the winning triangle (for tie ranks)
+};
+
+// Candidate (t,u,v) from record `wtri` of instance `inst`: closest wins; an exact-t tie goes to
+// the candidate the reference would have visited LAST (Q1 + Q2) -- looked up in the rank tables.
+JT_DEV void wide_accept(const JtDevScene& S, WideBest& B, float t, float u, float v, int inst, int elem, int wtri,
+                        uint32_t world_oct, uint32_t local_oct) {
+  if (B.inst >= 0 && t == B.t) {
+    bool later;
+    if (inst != B.inst) {
+      later = __ldg(S.inst_rank + (size_t)world_oct * S.num_instances + inst) >
+              __ldg(S.inst_rank + (size_t)world_oct * S.num_instances + B.inst);
+    } else {
+      later = __ldg(S.tri_rank + (size_t)local_oct * S.num_wtris + wtri) >
+              __ldg(S.tri_rank + (size_t)local_oct * S.num_wtris + B.wtri);
+    }
+    if (!later) return;
+  }
+  B.t = t; B.u = u; B.v = v; B.inst = inst; B.elem = elem; B.wtri = wtri;
+}
+
+// Shared traversal core. `root` is a wide node index; when `single_inst` >= 0 the walk starts
+// inside that instance's BLAS with the ray already in instance space (intersect_instance_bvh).
+JT_DEV void wide_walk(const JtDevScene& S, uint32_t root, f3 o, f3 d, float tmin, float tmax, int single_inst,
+                      WideBest& B) {
+  uint2 stack[JT_WIDE_STACK];
+  int sp = 0;
+  WideRay R, Rworld;
+  wide_ray_setup(R, o, d);
+  Rworld = R;
+  const uint32_t world_oct = R.rank_oct;
+  int cur_inst = single_inst;  // >= 0 while inside an instanced BLAS
+  int blas_sp = -1;            // stack height at BLAS entry (-1 = in the top level / single-instance walk)
+  uint2 ngroup = make_uint2(root, 0x80000000u), tgroup = make_uint2(0u, 0u);
+  float best_t = tmax;  // current acceptance bound (reference: ray.tmax shrinks with every hit)
+  for (;;) {
+    if (ngroup.y > 0x00FFFFFFu) {
+      uint32_t hits = ngroup.y;
+      uint32_t bit = 31u - (uint32_t)__clz(hits);
+      hits &= ~(1u << bit);
+      ngroup.y = hits;
+      if (hits > 0x00FFFFFFu) stack[sp++] = ngroup;
+      uint32_t slot = (bit - 24u) ^ R.oct;
+      uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
+      wide_node_hits(S.wnodes, ngroup.x + rel, R, tmin, best_t, &ngroup, &tgroup);
+    } else {
+      tgroup = ngroup;
+      ngroup = make_uint2(0u, 0u);
+    }
+    while (tgroup.y != 0u) {
+      uint32_t bit = (uint32_t)__ffs((int)tgroup.y) - 1u;
+      tgroup.y &= ~(1u << bit);
+      uint32_t wtri = tgroup.x + bit;
+      const float4* tp = S.wtris + 3 * (size_t)wtri;
+      float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
+      uint32_t flags = __float_as_uint(r2.w);
+      if (flags & 0x100u) {
+        // instance record: park the rest of the world-level work, switch to instance space
+        int inst = __float_as_int(r1.w);
+        if (tgroup.y != 0u) stack[sp++] = tgroup;
+        if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;
+        blas_sp = sp;
+        cur_inst = inst;
+        const JtInstanceRec& I = S.instances[inst];
+        wide_ray_setup(R, xform_point(I.inv, Rworld.o), xform_vector(I.inv, Rworld.d));
+        ngroup = make_uint2((uint32_t)S.shapes[I.shape].wide_root, 0x80000000u);
+        tgroup = make_uint2(0u, 0u);
+        break;
+      }
+      float t, u, v;
+      if (tri_test(R.o, R.d, tmin, best_t, f3{r0.x, r0.y, r0.z}, f3{r1.x, r1.y, r1.z}, f3{r2.x, r2.y, r2.z}, &t,
+                   &u, &v)) {
+        int inst = cur_inst >= 0 ? cur_inst : __float_as_int(r1.w);
+        if (flags & 1u) {
+          u = 1.0f - u;
+          v = 1.0f - v;
+        }
+        wide_accept(S, B, t, u, v, inst, __float_as_int(r0.w), (int)wtri, world_oct, R.rank_oct);
+        best_t = B.t;
+      }
+    }
+    if (ngroup.y <= 0x00FFFFFFu) {
+      if (sp == blas_sp) {  // the BLAS is exhausted: back to world space
+        blas_sp = -1;
+        cur_inst = -1;
+        R = Rworld;
+      }
+      if (sp == 0) break;
+      ngroup = stack[--sp];
+    }
+  }
+}
+
+JT_DEV DHit wide_scene(const JtDevScene& S, const DRay& ray) {
+  WideBest B{0.0f, 0.0f, 0.0f, -1, -1, -1};
+  if (S.wide_root >= 0) wide_walk(S, (uint32_t)S.wide_root, ray.o, ray.d, ray.tmin, ray.tmax, -1, B);
+  return DHit{B.t, B.u, B.v, B.inst, B.elem};
+}
+
+JT_DEV DHit wide_instance(const JtDevScene& S, int inst, const DRay& ray) {
+  const JtInstanceRec& I = S.instances[inst];
+  WideBest B{0.0f, 0.0f, 0.0f, -1, -1, -1};
+  int root = S.shapes[I.shape].wide_root;
+  if (root >= 0)
+    wide_walk(S, (uint32_t)root, xform_point(I.inv, ray.o), xform_vector(I.inv, ray.d), ray.tmin, ray.tmax, inst, B);
+  return DHit{B.t, B.u, B.v, B.inst, B.elem};
+}
+
+// ---- mode dispatch -------------------------------------------------------------------------------
+template <int MODE>
+JT_DEV DHit intersect_scene(const JtDevScene& S, const DRay& ray) {
+  if (MODE == MODE_REF) return ref_scene(S, ray);
+  return wide_scene(S, ray);
+}
+template <int MODE>
+JT_DEV DHit intersect_instance(const JtDevScene& S, int inst, const DRay& ray) {
+  if (MODE == MODE_REF) return ref_instance(S, inst, ray);
+  return wide_instance(S, inst, ray);
+}

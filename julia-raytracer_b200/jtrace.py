@@ -1,0 +1,91 @@
+"""`Jtrace.main` (src/jtrace.jl:31-116) with the render loop on the GPU.
+
+Same phases, same prints: load scene -> find camera -> build bvh -> make lights -> make state ->
+`samples / batch` calls of `trace_samples` -> get_image -> save_image."""
+from __future__ import annotations
+
+import math
+import time
+from typing import Optional, Union
+
+from .bvh import make_scene_bvh
+from .cli import Params, parse_cli_args
+from .lights import make_trace_lights
+from .scene import find_camera
+from .sceneio import load_scene, save_image
+from .trace import DeviceScene, get_image, make_trace_state, trace_samples
+
+
+def format_seconds(seconds: float) -> str:
+    """src/utils.jl:10-32."""
+    hours = math.floor(seconds / 3600)
+    minutes = math.floor((seconds - hours * 3600) / 60)
+    seconds = seconds - hours * 3600 - minutes * 60
+    i_seconds = math.floor(seconds)
+    ms = int(round((seconds - i_seconds) * 1000))
+    if hours == 0:
+        if minutes == 0:
+            return f"{i_seconds:02d}.{ms:03d}"
+        return f"{minutes:02d}:{i_seconds:02d}.{ms:03d}"
+    return f"{hours:02d}:{minutes:02d}:{i_seconds:02d}.{ms:03d}"
+
+
+def main(params: Union[str, Params, None], device: int = 0) -> Optional[dict]:
+    if isinstance(params, str):
+        params = parse_cli_args(params)
+    if params is None:
+        return None
+    if params.addsky:
+        print("addsky is not yet supported")
+        params.addsky = False
+    if params.envname != "":
+        print("envname is not yet supported")
+        params.envname = ""
+    if params.denoise:
+        print("denoise is not yet supported")
+        params.denoise = False
+    render_start = time.time()
+    print(f"loading scene {params.scene}...")
+    t0 = time.time()
+    scene = load_scene(params.scene, params.noparallel, verbose=True)
+    print(f"loaded scene in {format_seconds(time.time() - t0)}")
+    for note in scene.notes:
+        print(f"    note: {note}")
+    print("finding camera...")
+    params.camera = find_camera(scene, params.camera if isinstance(params.camera, str) else "")
+    print("building bvh...")
+    t0 = time.time()
+    bvh = make_scene_bvh(scene, params.highqualitybvh, params.noparallel)
+    print(f"built bvh in {format_seconds(time.time() - t0)}")
+    print("making lights...")
+    lights = make_trace_lights(scene, params)
+    print("uploading scene to the GPU...")
+    t0 = time.time()
+    dscene = DeviceScene(scene, bvh, lights, device)
+    print(f"uploaded in {format_seconds(time.time() - t0)}")
+    print("making state...")
+    state = make_trace_state(dscene, params)
+    print("tracing samples...")
+    sampling_start = time.time()
+    for _sample in range(1, params.samples + 1, max(params.batch, 1)):
+        batch_start = time.time()
+        trace_samples(state, dscene, bvh, lights, params, None, None, None)
+        now = time.time()
+        done = state.samples
+        print("sample %3d/%3d in %s ETC: %s" % (
+            done, params.samples, format_seconds(now - batch_start),
+            format_seconds((now - sampling_start) / max(done, 1) * (params.samples - done))))
+    dscene.synchronize()
+    render_s = time.time() - sampling_start
+    print("rendered in %s (%.3fs)" % (format_seconds(render_s), render_s))
+    state.sync()
+    c = dscene.counters()
+    rays = c["scene_rays"] + c["light_rays"]
+    print("    %.1f Msamples/s, %.1f Mrays/s (%d scene + %d light-probe rays)" % (
+        c["camera_paths"] / render_s / 1e6, rays / render_s / 1e6, c["scene_rays"], c["light_rays"]))
+    print("saving image...")
+    image = get_image(state)
+    save_image(params.output, image)
+    print("saved image to", params.output)
+    print(f"total time: {format_seconds(time.time() - render_start)}")
+    return dict(image=image, state=state, counters=c, render_seconds=render_s)

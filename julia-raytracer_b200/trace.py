@@ -1,0 +1,182 @@
+"""Host mirror of the reference's `Trace` module surface for the hot path (src/trace.jl):
+`make_trace_lights` (:117), `make_trace_state` (:189), `trace_samples` (:215), `get_image` (:676).
+
+`trace_samples` keeps the reference's signature (the three scratch-stack arguments are accepted
+and ignored) but the loop body runs in libjtrace_b200.so: accumulators stay on the device between
+calls and host arrays are refreshed on the final call (or on `state.sync()`)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+
+from . import _abi as A
+from . import _lib
+from .cli import Params
+from .flatten import FlatScene, SceneBvh, TraceLight
+from .lights import make_trace_lights  # noqa: F401  (re-exported like Trace.make_trace_lights)
+from .scene import SceneData
+
+
+def to_jt_params(params: Params, accumulate: int = 0) -> A.jt_params:
+    p = A.jt_params()
+    p.camera = int(params.camera) if not isinstance(params.camera, str) else 1
+    p.resolution, p.samples, p.bounces = params.resolution, params.samples, params.bounces
+    p.sampler, p.clamp = params.sampler, int(params.clamp)
+    p.nocaustics, p.envhidden, p.tentfilter = int(params.nocaustics), int(params.envhidden), int(params.tentfilter)
+    p.batch, p.bvhstacksize = params.batch, params.bvhstacksize
+    p.traversal = 1 if getattr(params, "gpu_traversal", "wide") == "reference" else 0
+    p.seed = int(getattr(params, "gpu_seed", 0))
+    p.accumulate = accumulate
+    return p
+
+
+class DeviceScene:
+    """(scene, bvh, lights) resident on one GPU: what `trace_samples` consumes."""
+
+    def __init__(self, scene: SceneData, bvh: SceneBvh, lights: List[TraceLight], device: int = 0):
+        self.L = _lib.lib()
+        self.flat = FlatScene(scene, bvh, lights)
+        h = C.c_void_p()
+        _lib.check(self.L.jt_scene_create(self.flat.byref(), device, C.byref(h)))
+        self.h = h
+        self.device = device
+        self.scene = scene
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.jt_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self) -> dict:
+        s = A.jt_scene_stats()
+        _lib.check(self.L.jt_scene_get_stats(self.h, C.byref(s)))
+        d = {k: int(getattr(s, k)) for k, _ in A.jt_scene_stats._fields_ if k != "_reserved"}
+        d["wide_depth_top"], d["wide_depth_blas"] = int(s._reserved[0]), int(s._reserved[1])
+        return d
+
+    def counters(self, reset: bool = False) -> dict:
+        c = A.jt_counters()
+        _lib.check(self.L.jt_scene_counters(self.h, C.byref(c), int(reset)))
+        return dict(camera_paths=int(c.camera_paths), scene_rays=int(c.scene_rays),
+                    light_rays=int(c.light_rays), kernel_launches=int(c.kernel_launches))
+
+    def synchronize(self):
+        _lib.check(self.L.jt_synchronize(self.h))
+
+    def elapsed_ms(self) -> float:
+        ms = C.c_float()
+        _lib.check(self.L.jt_elapsed_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    # -- parity hooks -------------------------------------------------------------------------
+    def intersect(self, rays: np.ndarray, traversal: int = 0) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=A.RAY_DTYPE)
+        hits = np.zeros(len(rays), A.HIT_DTYPE)
+        _lib.check(self.L.jt_intersect(self.h, rays.ctypes.data, len(rays), traversal, hits.ctypes.data))
+        return hits
+
+    def intersect_instance(self, rays: np.ndarray, instances: np.ndarray, traversal: int = 0) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=A.RAY_DTYPE)
+        instances = np.ascontiguousarray(instances, dtype=np.int64)
+        hits = np.zeros(len(rays), A.HIT_DTYPE)
+        _lib.check(self.L.jt_intersect_instance(self.h, rays.ctypes.data, instances.ctypes.data, len(rays),
+                                                traversal, hits.ctypes.data))
+        return hits
+
+    def sample_camera(self, jp: A.jt_params, width: int, height: int, ij, puv_luv) -> np.ndarray:
+        ij = np.ascontiguousarray(ij, np.int32)
+        r = np.ascontiguousarray(puv_luv, np.float32)
+        rays = np.zeros(len(ij), A.RAY_DTYPE)
+        _lib.check(self.L.jt_sample_camera(self.h, C.byref(jp), width, height, ij.ctypes.data, r.ctypes.data,
+                                           len(ij), rays.ctypes.data))
+        return rays
+
+
+class TraceState:
+    """`TraceState` (src/trace.jl:87-96): host arrays in the reference's layouts + the device twin."""
+
+    def __init__(self, dscene: DeviceScene, params: Params, accumulate: int = 0):
+        self.dscene = dscene
+        self.L = dscene.L
+        self.jp = to_jt_params(params, accumulate)
+        h = C.c_void_p()
+        _lib.check(self.L.jt_state_create(dscene.h, C.byref(self.jp), C.byref(h)))
+        self.h = h
+        w, hh, s = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(self.L.jt_state_size(self.h, C.byref(w), C.byref(hh), C.byref(s)))
+        self.width, self.height = w.value, hh.value
+        n = self.width * self.height
+        self.image = np.zeros((n, 4), np.float32)   # Vector{Vec4f}
+        self.albedo = np.zeros((n, 3), np.float32)  # Vector{Vec3f}
+        self.normal = np.zeros((n, 3), np.float32)
+        self.hits = np.zeros(n, np.int64)           # Vector{Int}
+        self.denoised = np.zeros((0, 4), np.float32)
+
+    @property
+    def samples(self) -> int:
+        s = C.c_int32()
+        _lib.check(self.L.jt_state_size(self.h, None, None, C.byref(s)))
+        return s.value
+
+    def sync(self) -> "TraceState":
+        """Refresh the host arrays from the device accumulators."""
+        _lib.check(self.L.jt_state_download(self.h, self.image.ctypes.data, self.albedo.ctypes.data,
+                                            self.normal.ctypes.data, self.hits.ctypes.data))
+        return self
+
+    def reset(self):
+        _lib.check(self.L.jt_state_reset(self.h))
+
+    def device_buffers(self):
+        a, b, c, d, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        _lib.check(self.L.jt_state_device_buffers(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d), C.byref(n)))
+        return dict(image=a.value, albedo=b.value, normal=c.value, hits=d.value, count=n.value)
+
+    def set_samples(self, samples: int):
+        _lib.check(self.L.jt_state_set_samples(self.h, samples))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.jt_state_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def make_trace_state(dscene: DeviceScene, params: Params, accumulate: int = 0) -> TraceState:
+    """src/trace.jl:189-213 (sizes from resolution and the camera aspect; zeroed buffers)."""
+    return TraceState(dscene, params, accumulate)
+
+
+def trace_samples(state: TraceState, scene: DeviceScene, bvh=None, lights=None, params: Optional[Params] = None,
+                  bvh_stacks=None, bvh_sub_stacks=None, volume_stacks=None) -> None:
+    """src/trace.jl:215-274. `bvh` and `lights` already live inside `scene` (a DeviceScene); the
+    scratch stacks are ignored. Enqueues `params.batch` more samples per pixel and returns."""
+    jp = to_jt_params(params, state.jp.accumulate) if params is not None else state.jp
+    L = state.L
+    _lib.check(L.jt_trace_samples(scene.h, state.h, C.byref(jp)))
+    if state.samples >= jp.samples:
+        state.sync()
+
+
+def trace_sample_range(state: TraceState, scene: DeviceScene, params: Params, begin: int, end: int) -> None:
+    """The sharding unit: samples [begin, end) of every pixel."""
+    jp = to_jt_params(params, state.jp.accumulate)
+    _lib.check(state.L.jt_trace_sample_range(scene.h, state.h, C.byref(jp), begin, end))
+
+
+def get_image(state: TraceState) -> np.ndarray:
+    """src/trace.jl:676-690: (H, W, 4) linear RGBA view of state.image."""
+    return state.image.reshape(state.height, state.width, 4)

@@ -1,0 +1,108 @@
+// TEST INFRASTRUCTURE -- CPU single-stepping of the device code (see emu_shims.h).
+#include "emu_shims.h"
+#define JT_DEV static inline
+#include "../../julia-raytracer_b200/csrc/jt_dev_trace.cuh"
+
+#include <omp.h>
+#include <vector>
+
+struct Emu {
+  JtStagedScene staged;
+  JtDevScene dev;
+};
+
+extern "C" {
+#define EMU_API __attribute__((visibility("default")))
+
+EMU_API const char* emu_last_error() { return jt_last_error(); }
+
+EMU_API void* emu_create(const jt_scene_desc* d) {
+  Emu* e = new Emu();
+  if (jt_stage_scene(d, &e->staged) != 0) {
+    delete e;
+    return nullptr;
+  }
+  JtStagedScene& S = e->staged;
+  JtStagedPointers P;
+  P.ref_nodes = S.ref_nodes.data(); P.ref_prims = S.ref_prims.data(); P.shapes = S.shape_recs.data();
+  P.positions = S.positions.data(); P.normals = S.normals.data(); P.texcoords = S.texcoords.data();
+  P.colors = S.colors.data(); P.elements = S.elements.data(); P.instances = S.inst_recs.data();
+  P.materials = S.mats.data(); P.textures = S.texs.data(); P.texels_f = S.texels_f.data();
+  P.texels_b = S.texels_b.data(); P.srgb_lut = S.lut.data(); P.environments = S.envs.data();
+  P.lights = S.lights.data(); P.light_cdf = S.cdf.data(); P.cameras = S.cams.data();
+  P.wnodes = (const float4*)S.wide.nodes.data(); P.wtris = (const float4*)S.wide.tris.data();
+  P.tri_rank = S.tri_rank.data(); P.inst_rank = S.inst_rank.data();
+  jt_fill_dev_scene(S, P, &e->dev);
+  return e;
+}
+EMU_API void emu_destroy(void* h) { delete (Emu*)h; }
+
+EMU_API void emu_stats(void* h, int64_t* out) {
+  Emu* e = (Emu*)h;
+  out[0] = (int64_t)e->staged.wide.nodes.size();
+  out[1] = (int64_t)e->staged.wide.tris.size();
+  out[2] = e->staged.wide.inlined_instances;
+  out[3] = e->staged.wide.instanced_instances;
+  out[4] = e->staged.depth;
+  out[5] = e->staged.blas_depth;
+}
+
+static void put_hit(jt_hit* o, const DHit& h) {
+  memset(o, 0, sizeof(*o));
+  if (h.inst >= 0) {
+    o->instance = h.inst + 1; o->element = h.elem + 1; o->uv[0] = h.u; o->uv[1] = h.v; o->distance = h.t; o->hit = 1;
+  } else {
+    o->instance = -1; o->element = -1;
+  }
+}
+
+EMU_API void emu_intersect(void* h, const jt_ray* rays, int64_t n, int traversal, jt_hit* out) {
+  Emu* e = (Emu*)h;
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (int64_t i = 0; i < n; i++) {
+    DRay r{f3{rays[i].o[0], rays[i].o[1], rays[i].o[2]}, f3{rays[i].d[0], rays[i].d[1], rays[i].d[2]}, rays[i].tmin, rays[i].tmax};
+    put_hit(out + i, traversal == 1 ? intersect_scene<MODE_REF>(e->dev, r) : intersect_scene<MODE_WIDE>(e->dev, r));
+  }
+}
+EMU_API void emu_intersect_instance(void* h, const jt_ray* rays, const int64_t* inst, int64_t n, int traversal, jt_hit* out) {
+  Emu* e = (Emu*)h;
+#pragma omp parallel for schedule(dynamic, 1024)
+  for (int64_t i = 0; i < n; i++) {
+    DRay r{f3{rays[i].o[0], rays[i].o[1], rays[i].o[2]}, f3{rays[i].d[0], rays[i].d[1], rays[i].d[2]}, rays[i].tmin, rays[i].tmax};
+    put_hit(out + i, traversal == 1 ? intersect_instance<MODE_REF>(e->dev, (int)inst[i] - 1, r)
+                                    : intersect_instance<MODE_WIDE>(e->dev, (int)inst[i] - 1, r));
+  }
+}
+
+// trace_sample for samples [begin, end) of every pixel into host accumulators (float4 image/albedo/normal, int hits)
+EMU_API void emu_trace_range(void* h, const jt_params* p, int width, int height, int begin, int end, float* image,
+                             float* albedo, float* normal, int* hits, uint64_t* counters) {
+  Emu* e = (Emu*)h;
+  DevParams P;
+  P.camera = p->camera - 1; P.width = width; P.height = height; P.bounces = p->bounces; P.sampler = p->sampler;
+  P.clamp = p->clamp; P.nocaustics = p->nocaustics; P.envhidden = p->envhidden; P.tentfilter = p->tentfilter;
+  P.accumulate = p->accumulate; P.seed = p->seed;
+  DevState st{(float4*)image, (float4*)albedo, (float4*)normal, hits};
+  bool has_env = e->dev.num_environments != 0;
+  uint64_t scene_rays = 0, light_rays = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : scene_rays, light_rays)
+  for (int j = 0; j < height; j++)
+    for (int i = 0; i < width; i++) {
+      int idx = width * j + i;
+      for (int s = begin; s < end; s++) {
+        PathCounters cnt{0u, 0u};
+        Rng rng{jt_rng_key(P.seed, (uint32_t)idx, (uint32_t)s), 0u};
+        f2 puv = rng.next2();
+        f2 luv = rng.next2();
+        DRay ray = sample_camera(e->dev.cameras[P.camera], i, j, width, height, puv, luv, P.tentfilter != 0);
+        TraceOut r = p->traversal == 1
+                         ? (P.sampler == 1 ? trace_path<MODE_REF>(e->dev, ray, P, rng, cnt) : trace_naive<MODE_REF>(e->dev, ray, P, rng, cnt))
+                         : (P.sampler == 1 ? trace_path<MODE_WIDE>(e->dev, ray, P, rng, cnt) : trace_naive<MODE_WIDE>(e->dev, ray, P, rng, cnt));
+        accumulate_sample(st, P, has_env, idx, s, r, ray.d);
+        scene_rays += cnt.scene_rays;
+        light_rays += cnt.light_rays;
+      }
+    }
+  if (counters) { counters[0] += scene_rays; counters[1] += light_rays; }
+}
+}

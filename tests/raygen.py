@@ -1,0 +1,39 @@
+"""Seeded ray sets for the identical-rays parity tests (TEST INFRASTRUCTURE)."""
+from __future__ import annotations
+
+import numpy as np
+
+import orc
+
+A = orc.A
+
+
+def camera_rays(oracle, params, width, height, n, seed=0):
+    rng = np.random.default_rng(seed)
+    ij = np.stack([rng.integers(0, width, n), rng.integers(0, height, n)], axis=1).astype(np.int32)
+    r = (rng.integers(0, 1 << 24, (n, 4)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+    return oracle.sample_camera(params, width, height, ij, r)
+
+
+def secondary_rays(rays, hits, seed=1):
+    """One random-direction ray from every hit point (what bounce rays look like)."""
+    rng = np.random.default_rng(seed)
+    m = hits["hit"] != 0
+    o = rays["o"][m] + rays["d"][m] * hits["distance"][m][:, None]
+    d = rng.normal(size=(int(m.sum()), 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    out = np.zeros(len(o), A.RAY_DTYPE)
+    out["o"], out["d"] = o.astype(np.float32), d.astype(np.float32)
+    out["tmin"], out["tmax"] = np.float32(1e-4), np.float32(np.inf)
+    return out
+
+
+def compare_hits(a, b):
+    """-> dict(n, id_mismatch, t_mismatch, uv_mismatch, max_rel_t) ; ids must be bit-equal."""
+    ids = (a["instance"] != b["instance"]) | (a["element"] != b["element"]) | (a["hit"] != b["hit"])
+    same = ~ids
+    t_bits = a["distance"][same].view(np.uint32) != b["distance"][same].view(np.uint32)
+    uv_bits = (a["uv"][same].view(np.uint32) != b["uv"][same].view(np.uint32)).any(axis=1)
+    rel = np.abs(a["distance"][same] - b["distance"][same]) / np.maximum(np.abs(b["distance"][same]), 1e-30)
+    return dict(n=len(a), id_mismatch=int(ids.sum()), t_mismatch=int(t_bits.sum()), uv_mismatch=int(uv_bits.sum()),
+                max_rel_t=float(rel.max()) if len(rel) else 0.0)
