@@ -37,3 +37,21 @@ def compare_hits(a, b):
     rel = np.abs(a["distance"][same] - b["distance"][same]) / np.maximum(np.abs(b["distance"][same]), 1e-30)
     return dict(n=len(a), id_mismatch=int(ids.sum()), t_mismatch=int(t_bits.sum()), uv_mismatch=int(uv_bits.sum()),
                 max_rel_t=float(rel.max()) if len(rel) else 0.0)
+
+
+def check_wide_vs_reference(wide, ref, max_rate=1e-4):
+    """Wide-BVH mode contract: identical to the reference-order result except for the documented
+    residual class (DESIGN.md "exactness"): the reference's slab test (src/geometry.jl:96-105) is not
+    conservative and occasionally culls the node that holds the true closest hit; the wide BVH's
+    conservative boxes keep it. Every mismatch must therefore be a STRICTLY CLOSER hit (or a hit where
+    the reference reports a miss), and the rate must stay below max_rate. t/u/v of agreeing ids are
+    bit-identical."""
+    r = compare_hits(wide, ref)
+    assert r["t_mismatch"] == 0 and r["uv_mismatch"] == 0, r
+    bad = (wide["instance"] != ref["instance"]) | (wide["element"] != ref["element"]) | (wide["hit"] != ref["hit"])
+    if bad.any():
+        w, o = wide[bad], ref[bad]
+        closer = (w["hit"] == 1) & ((o["hit"] == 0) | (w["distance"] < o["distance"]))
+        assert closer.all(), (w[~closer], o[~closer])
+        assert bad.sum() <= max(1, int(max_rate * len(wide))), r
+    return r

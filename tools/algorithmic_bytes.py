@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Freeze the algorithmic bytes per ray / per sample of SURVEY.md §8(d) from ORACLE counters:
+    B_ray = 32 (ray in) + 24 (hit out) + 32*N_nodes + 48*N_inst + 36*N_tri + 48*N_quad
+counted under the reference's traversal order on the reference's binary BVH over a full render at
+reduced resolution/spp (per-sample figures do not depend on either). Writes
+profiles/algorithmic_bytes.json, which bench.py multiplies by the samples one launch processes."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import orc  # noqa: E402
+
+out = {}
+for scene, sampler, res, spp in [("cornellbox", "naive", 360, 8), ("cornellbox", "path", 360, 8),
+                                 ("features1", "path", 640, 4), ("materials1", "path", 640, 4),
+                                 ("classroom", "path", 640, 4), ("ecosys", "path", 480, 2)]:
+    sc = orc.jt.load_scene(os.path.join(ROOT, "assets", "scenes", f"{scene}.jtscene"))
+    o = orc.Oracle(sc)
+    p = orc.make_params(resolution=res, samples=spp, batch=spp, sampler=1 if sampler == "path" else 2)
+    w, h = o.make_state(p)
+    o.trace_samples(p)
+    c = o.counters()
+    rays = c["scene_rays"] + c["light_rays"]
+    b = orc.algorithmic_bytes(c)
+    out[f"{scene}_{sampler}"] = {
+        "bytes_per_sample": b / c["camera_paths"] + 16.0, "bytes_per_ray": b / rays,
+        "rays_per_sample": rays / c["camera_paths"], "scene_rays_per_sample": c["scene_rays"] / c["camera_paths"],
+        "light_rays_per_sample": c["light_rays"] / c["camera_paths"],
+        "nodes_per_ray": (c["tlas_nodes"] + c["blas_nodes"]) / rays, "instance_visits_per_ray": c["instance_visits"] / rays,
+        "tri_tests_per_ray": c["tri_tests"] / rays, "quad_tests_per_ray": c["quad_tests"] / rays,
+        "measured_on": f"{w}x{h} x {spp} spp, oracle, reference traversal order", "source": "profiles/algorithmic_bytes.json"}
+    print(scene, sampler, json.dumps(out[f"{scene}_{sampler}"]), flush=True)
+os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "profiles", "algorithmic_bytes.json"), "w"), indent=1)
