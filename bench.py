@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--resolution", type=int, default=1280)
     ap.add_argument("--spp-per-step", type=int, default=8)
     ap.add_argument("--traversal", default="wide", choices=["wide", "reference"])
+    ap.add_argument("--integrator", default="wavefront", choices=["wavefront", "megakernel"])
     ap.add_argument("--cpu-spp", type=int, default=2, help="samples per pixel of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -207,7 +208,7 @@ def main():
     total_steps = args.warmup + args.steps
     params = jt.Params(scene=args.scene, resolution=args.resolution, samples=1 << 30, batch=spp,
                        sampler=1 if args.sampler == "path" else 2, camera=jt.find_camera(scene, ""),
-                       gpu_traversal=args.traversal)
+                       gpu_traversal=args.traversal, gpu_integrator=args.integrator)
     # sum mode: what the cross-GPU reduce adds up; rank r takes global sample indices
     # [ (step*world + r)*spp, +spp ): disjoint counter-RNG streams by construction
     state = trace.make_trace_state(dscene, params, accumulate=1)
@@ -287,7 +288,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": wall_s / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "reference scene (packed asset assets/scenes, missing-asset rule of SURVEY §8d), counter-based RNG",
-            "config": {"workload": workload_name(args, w, h), "traversal": args.traversal,
+            "config": {"workload": workload_name(args, w, h), "traversal": args.traversal, "integrator": args.integrator,
                        "sharding": f"global sample indices strided over {world} rank(s); scene replicated; "
                                    f"one NCCL reduce of the RGBA sum buffer at job end" if world > 1 else "single GPU",
                        "l2": "256 MB buffer written between timed iterations (L2 flush); the scene itself "
@@ -330,7 +331,7 @@ def main():
                 traffic = json.load(open(tp)).get(f"{args.scene}_{args.sampler}_{args.traversal}")
             line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                                "kernel": "k_trace_mega", "algorithmic_bytes_per_sample": per_sample["bytes_per_sample"],
+                                "kernel": "k_trace_mega" if args.integrator == "megakernel" else "k_wf_extend+k_wf_shade+k_wf_probe (one wavefront step; launches per step vary with path depth)", "algorithmic_bytes_per_sample": per_sample["bytes_per_sample"],
                                 "algorithmic_bytes_source": per_sample.get("source", "profiles/algorithmic_bytes.json"),
                                 "note": "work-normalised to the REFERENCE algorithm (SURVEY §8d formula); the scene is "
                                         "L2-resident and the wide BVH touches fewer bytes, so this can exceed DRAM counters"}

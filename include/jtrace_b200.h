@@ -145,7 +145,8 @@ typedef struct {
   uint64_t seed;        /* counter-based RNG seed (jt_rng.h) */
   int32_t accumulate;   /* 0 = running-mean lerp exactly like src/trace.jl:631-647 (Q13)
                            1 = plain sums (divide at download) -- what multi-GPU sharding reduces */
-  int32_t _reserved[7];
+  int32_t integrator;   /* 0 = wavefront (queues + compaction, default), 1 = one-thread-per-pixel megakernel */
+  int32_t _reserved[6];
 } jt_params;
 
 /* Ray3f (src/geometry.jl:36-40) -- 32 B */

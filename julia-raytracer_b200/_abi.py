@@ -80,7 +80,8 @@ class jt_params(C.Structure):
                 ("bounces", C.c_int32), ("sampler", C.c_int32), ("clamp", C.c_int32),
                 ("nocaustics", C.c_int32), ("envhidden", C.c_int32), ("tentfilter", C.c_int32),
                 ("batch", C.c_int32), ("bvhstacksize", C.c_int32), ("traversal", C.c_int32),
-                ("seed", C.c_uint64), ("accumulate", C.c_int32), ("_reserved", C.c_int32 * 7)]
+                ("seed", C.c_uint64), ("accumulate", C.c_int32), ("integrator", C.c_int32),
+                ("_reserved", C.c_int32 * 6)]
 
 
 class jt_ray(C.Structure):

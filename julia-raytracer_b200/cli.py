@@ -52,6 +52,10 @@ def make_parser() -> argparse.ArgumentParser:
                    choices=["wide", "reference"],
                    help="wide = quantised 8-wide BVH (fast); reference = the host-built binary "
                         "BVH walked in the reference's own order (parity mode)")
+    p.add_argument("--gpu-integrator", dest="gpu_integrator", type=str, default="wavefront",
+                   choices=["wavefront", "megakernel"],
+                   help="wavefront = staged kernels over compacted, material-sorted queues (default); "
+                        "megakernel = one thread per pixel running the whole trace_sample")
     return p
 
 
@@ -77,6 +81,7 @@ class Params:  # src/cli.jl:90-108
     bvhstacksize: int = 128
     gpu_seed: int = 0
     gpu_traversal: str = "wide"
+    gpu_integrator: str = "wavefront"
 
     @staticmethod
     def from_args(ns: argparse.Namespace) -> "Params":

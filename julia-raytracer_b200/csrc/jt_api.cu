@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "jt_dev_trace.cuh"
+#include "jt_dev_wavefront.cuh"
 #include "jt_internal.h"
 
 // =================================================================================================
@@ -68,6 +69,15 @@ struct jt_state {
   int width = 0, height = 0, samples = 0;
   int accumulate = 0;
   DevState dev;
+  // wavefront integrator (allocated on first use)
+  bool wf_ready = false;
+  WfBuffers wf;
+  std::vector<void*> wf_allocs;
+  int* h_counts = nullptr;  // pinned mirror of wf.counts
+  // download staging (allocated on first download)
+  void* d_pack = nullptr;
+  void* h_pack = nullptr;
+  uint64_t wf_iterations = 0;
 };
 
 template <class T>
@@ -318,6 +328,7 @@ static int check_params(jt_scene* sc, const jt_params* p) {
   if (p->resolution < 1 || p->resolution > 32768) return jt_set_error(JT_ERR_INVALID, "bad resolution %d", p->resolution);
   if (p->traversal != 0 && p->traversal != 1) return jt_set_error(JT_ERR_INVALID, "traversal must be 0 (wide) or 1 (reference)");
   if (p->accumulate != 0 && p->accumulate != 1) return jt_set_error(JT_ERR_INVALID, "accumulate must be 0 or 1");
+  if (p->integrator != 0 && p->integrator != 1) return jt_set_error(JT_ERR_INVALID, "integrator must be 0 (wavefront) or 1 (megakernel)");
   if (p->sampler == 1 && sc->dev.num_lights == 0)
     return jt_set_error(JT_ERR_UNSUPPORTED, "path sampler on a scene without lights: sample_lights indexes an empty array in the reference");
   return JT_OK;
@@ -377,6 +388,10 @@ extern "C" void jt_state_destroy(jt_state* st) {
   cudaSetDevice(st->scene->device);
   cudaStreamSynchronize(st->scene->stream);
   cudaFree(st->dev.image); cudaFree(st->dev.albedo); cudaFree(st->dev.normal); cudaFree(st->dev.hits);
+  for (void* p : st->wf_allocs) cudaFree(p);
+  if (st->h_counts) cudaFreeHost(st->h_counts);
+  if (st->d_pack) cudaFree(st->d_pack);
+  if (st->h_pack) cudaFreeHost(st->h_pack);
   delete st;
 }
 
@@ -410,29 +425,32 @@ extern "C" int jt_state_download(jt_state* st, float* image, float* albedo, floa
   jt_scene* sc = st->scene;
   JT_CUDA(cudaSetDevice(sc->device));
   long long n = (long long)st->width * st->height;
-  float *di = nullptr, *da = nullptr, *dn = nullptr;
-  long long* dh = nullptr;
-  int rc = JT_OK;
-  auto fail = [&](cudaError_t e) { rc = jt_set_error(JT_ERR_CUDA, "jt_state_download: %s", cudaGetErrorString(e)); };
-  cudaError_t e;
-  if (image && (e = cudaMalloc((void**)&di, n * 16)) != cudaSuccess) fail(e);
-  if (!rc && albedo && (e = cudaMalloc((void**)&da, n * 12)) != cudaSuccess) fail(e);
-  if (!rc && normal && (e = cudaMalloc((void**)&dn, n * 12)) != cudaSuccess) fail(e);
-  if (!rc && hits && (e = cudaMalloc((void**)&dh, n * 8)) != cudaSuccess) fail(e);
-  if (!rc) {
-    float scale = (st->accumulate == 1 && st->samples > 0) ? 1.0f / (float)st->samples : 1.0f;
-    k_finalize<<<(unsigned)((n + 255) / 256), 256, 0, sc->stream>>>(st->dev.image, st->dev.albedo, st->dev.normal,
-                                                                     st->dev.hits, n, scale, di, da, dn, dh);
-    sc->launches++;
-    if ((e = cudaGetLastError()) != cudaSuccess) fail(e);
-    if (!rc && image && (e = cudaMemcpyAsync(image, di, n * 16, cudaMemcpyDeviceToHost, sc->stream)) != cudaSuccess) fail(e);
-    if (!rc && albedo && (e = cudaMemcpyAsync(albedo, da, n * 12, cudaMemcpyDeviceToHost, sc->stream)) != cudaSuccess) fail(e);
-    if (!rc && normal && (e = cudaMemcpyAsync(normal, dn, n * 12, cudaMemcpyDeviceToHost, sc->stream)) != cudaSuccess) fail(e);
-    if (!rc && hits && (e = cudaMemcpyAsync(hits, dh, n * 8, cudaMemcpyDeviceToHost, sc->stream)) != cudaSuccess) fail(e);
-    if ((e = cudaStreamSynchronize(sc->stream)) != cudaSuccess && !rc) fail(e);
-  }
-  cudaFree(di); cudaFree(da); cudaFree(dn); cudaFree(dh);
-  return rc;
+  // persistent staging: one packed device buffer + one pinned host buffer (48 B per pixel)
+  if (!st->d_pack) JT_CUDA(cudaMalloc(&st->d_pack, (size_t)n * 48));
+  if (!st->h_pack) JT_CUDA(cudaHostAlloc(&st->h_pack, (size_t)n * 48, cudaHostAllocDefault));
+  char* dp = (char*)st->d_pack;
+  float* di = (float*)dp;
+  float* da = (float*)(dp + n * 16);
+  float* dn = (float*)(dp + n * 28);
+  long long* dh = (long long*)(dp + n * 40);
+  float scale = (st->accumulate == 1 && st->samples > 0) ? 1.0f / (float)st->samples : 1.0f;
+  k_finalize<<<(unsigned)((n + 255) / 256), 256, 0, sc->stream>>>(st->dev.image, st->dev.albedo, st->dev.normal,
+                                                                   st->dev.hits, n, scale, image ? di : nullptr,
+                                                                   albedo ? da : nullptr, normal ? dn : nullptr,
+                                                                   hits ? dh : nullptr);
+  sc->launches++;
+  JT_CUDA(cudaGetLastError());
+  char* hp = (char*)st->h_pack;
+  if (image) JT_CUDA(cudaMemcpyAsync(hp, di, (size_t)n * 16, cudaMemcpyDeviceToHost, sc->stream));
+  if (albedo) JT_CUDA(cudaMemcpyAsync(hp + n * 16, da, (size_t)n * 12, cudaMemcpyDeviceToHost, sc->stream));
+  if (normal) JT_CUDA(cudaMemcpyAsync(hp + n * 28, dn, (size_t)n * 12, cudaMemcpyDeviceToHost, sc->stream));
+  if (hits) JT_CUDA(cudaMemcpyAsync(hp + n * 40, dh, (size_t)n * 8, cudaMemcpyDeviceToHost, sc->stream));
+  JT_CUDA(cudaStreamSynchronize(sc->stream));
+  if (image) memcpy(image, hp, (size_t)n * 16);
+  if (albedo) memcpy(albedo, hp + n * 16, (size_t)n * 12);
+  if (normal) memcpy(normal, hp + n * 28, (size_t)n * 12);
+  if (hits) memcpy(hits, hp + n * 40, (size_t)n * 8);
+  return JT_OK;
 }
 
 // =================================================================================================
@@ -449,18 +467,92 @@ static DevParams dev_params(const jt_params* p, const jt_state* st) {
   return P;
 }
 
+static int wf_prepare(jt_scene* sc, jt_state* st) {
+  if (st->wf_ready) return JT_OK;
+  size_t n = (size_t)st->width * st->height;
+  WfBuffers& B = st->wf;
+  memset(&B, 0, sizeof(B));
+  B.n = (int)n;
+  auto alloc = [&](void** out, size_t bytes) -> int {
+    JT_CUDA(cudaMalloc(out, bytes));
+    st->wf_allocs.push_back(*out);
+    return JT_OK;
+  };
+  int rc;
+  if ((rc = alloc((void**)&B.ray0, n * 16)) || (rc = alloc((void**)&B.ray1, n * 16)) || (rc = alloc((void**)&B.hit0, n * 16)) ||
+      (rc = alloc((void**)&B.wgt, n * 16)) || (rc = alloc((void**)&B.rad, n * 16)) || (rc = alloc((void**)&B.bsdf, n * 16)) ||
+      (rc = alloc((void**)&B.alb, n * 16)) || (rc = alloc((void**)&B.nrm, n * 16)) || (rc = alloc((void**)&B.med0, n * 16)) ||
+      (rc = alloc((void**)&B.med1, n * 16)) || (rc = alloc((void**)&B.ctl, n * 16)) ||
+      (rc = alloc((void**)&B.q_ext[0], n * 4)) || (rc = alloc((void**)&B.q_ext[1], n * 4)) ||
+      (rc = alloc((void**)&B.q_shade, n * 4 * WF_NKEY)) || (rc = alloc((void**)&B.q_probe, n * 4)) ||
+      (rc = alloc((void**)&B.counts, WF_C_TOTAL * 4)))
+    return rc;
+  JT_CUDA(cudaHostAlloc((void**)&st->h_counts, WF_C_TOTAL * 4, cudaHostAllocDefault));
+  st->wf_ready = true;
+  return JT_OK;
+}
+
+// Host-driven wavefront loop: generate, then (extend, shade, probe, advance) until the extend queue is
+// empty. Queue sizes stay on the device; the host only polls the next-queue length every few iterations.
+template <int MODE>
+static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int begin, int end) {
+  int rc = wf_prepare(sc, st);
+  if (rc) return rc;
+  WfBuffers& B = st->wf;
+  const int n = B.n;
+  cudaStream_t q = sc->stream;
+  k_wf_generate<<<(n + 255) / 256, 256, 0, q>>>(sc->dev, B, P, begin, end, sc->d_counters);
+  sc->launches++;
+  const unsigned g_ext = (unsigned)((n + 127) / 128), g_shade = (unsigned)((n + 32 * WF_NKEY + 127) / 128);
+  int cur = 0;
+  int remaining = n;
+  const int poll_every = 4;
+  for (int it = 0;; it++) {
+    int next = cur ^ 1;
+    // grids sized from the last polled queue length (an upper bound until the next poll: queues only
+    // shrink, because every slot appears at most once per iteration)
+    unsigned ge = (unsigned)((remaining + 127) / 128), gs = (unsigned)((remaining + 32 * WF_NKEY + 127) / 128);
+    (void)g_ext; (void)g_shade;
+    k_wf_extend<MODE><<<ge, 128, 0, q>>>(sc->dev, B, cur, sc->d_counters);
+    if (P.sampler == 1) {
+      k_wf_shade<1><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+      k_wf_probe<MODE><<<ge, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+      sc->launches += 4;
+    } else {
+      k_wf_shade<2><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+      sc->launches += 3;
+    }
+    k_wf_advance<<<1, 32, 0, q>>>(B, cur);
+    st->wf_iterations++;
+    cur = next;
+    if ((it + 1) % poll_every == 0) {
+      JT_CUDA(cudaMemcpyAsync(st->h_counts, B.counts, WF_C_TOTAL * 4, cudaMemcpyDeviceToHost, q));
+      JT_CUDA(cudaStreamSynchronize(q));
+      remaining = st->h_counts[WF_C_EXT0 + cur];
+      if (remaining == 0) break;
+    }
+  }
+  JT_CUDA(cudaGetLastError());
+  return JT_OK;
+}
+
 static int launch_range(jt_scene* sc, jt_state* st, const jt_params* p, int begin, int end) {
   if (end <= begin) return JT_OK;
   DevParams P = dev_params(p, st);
-  dim3 grid((unsigned)((st->width + 15) / 16), (unsigned)((st->height + 7) / 8));
   if (!sc->timing_open) {
     JT_CUDA(cudaEventRecord(sc->ev_start, sc->stream));
     sc->timing_open = true;
   }
-  if (p->traversal == 1) k_trace_mega<MODE_REF><<<grid, 128, 0, sc->stream>>>(sc->dev, st->dev, P, begin, end, sc->d_counters);
-  else k_trace_mega<MODE_WIDE><<<grid, 128, 0, sc->stream>>>(sc->dev, st->dev, P, begin, end, sc->d_counters);
-  sc->launches++;
-  JT_CUDA(cudaGetLastError());
+  if (p->integrator == 1) {
+    dim3 grid((unsigned)((st->width + 15) / 16), (unsigned)((st->height + 7) / 8));
+    if (p->traversal == 1) k_trace_mega<MODE_REF><<<grid, 128, 0, sc->stream>>>(sc->dev, st->dev, P, begin, end, sc->d_counters);
+    else k_trace_mega<MODE_WIDE><<<grid, 128, 0, sc->stream>>>(sc->dev, st->dev, P, begin, end, sc->d_counters);
+    sc->launches++;
+    JT_CUDA(cudaGetLastError());
+  } else {
+    int rc = p->traversal == 1 ? launch_wavefront<MODE_REF>(sc, st, P, begin, end) : launch_wavefront<MODE_WIDE>(sc, st, P, begin, end);
+    if (rc) return rc;
+  }
   JT_CUDA(cudaEventRecord(sc->ev_stop, sc->stream));
   return JT_OK;
 }

@@ -1,0 +1,448 @@
+// jt_dev_wavefront.cuh -- the wavefront form of trace_samples (src/trace.jl:215-649).
+//
+// The megakernel (k_trace_mega) executes one whole trace_sample per thread; ncu shows 5.65 of 32
+// lanes active per warp instruction on classroom (profiles/r01). Here the same arithmetic, the same
+// RNG streams and the same per-pixel sample order are reorganised into stages that run as separate
+// kernels over compacted queues of path slots:
+//
+//   generate : slot = pixel; every slot starts its first sample (camera ray)             -> q_extend
+//   extend   : closest hit for every queued ray (intersect_scene_bvh)                     -> q_shade[key]
+//              key = material type of the hit instance, or MISS: material-sorted shading queues
+//   shade    : miss -> environment; volume distance sampling; eval position / normal / material;
+//              opacity pass-through; emission; BSDF-or-light direction sampling; delta lobes and the
+//              naive sampler finish their bounce here                            -> q_probe | q_extend
+//   probe    : sample_lights_pdf (the chained intersect_instance_bvh probes), MIS weight,
+//              Russian roulette                                                           -> q_extend
+// A slot that terminates a sample accumulates it (running mean or sum) and regenerates the next
+// sample of ITS pixel in place, so samples of one pixel are still accumulated in order (Q13) with
+// no atomics on the image. Queue appends are warp-aggregated: one atomicAdd per warp per queue,
+// lane offsets from ballot / match_any masks.
+#pragma once
+#include "jt_dev_trace.cuh"
+
+#define WF_NKEY 9     /* material types 0..7 + miss */
+#define WF_KEY_MISS 8
+// counter slots (ints)
+#define WF_C_EXT0 0
+#define WF_C_EXT1 1
+#define WF_C_PROBE 2
+#define WF_C_SHADE 4  /* .. WF_C_SHADE + WF_NKEY */
+#define WF_C_TOTAL 16
+
+// ctl.z flags
+#define WF_F_MEDIUM 1u  /* cur_volume != 0 */
+#define WF_F_HIT 2u     /* first-hit outputs valid */
+#define WF_F_VOLSCAT 4u /* this bounce is an in-volume scattering event (probe stage uses eval_scattering data) */
+
+struct WfBuffers {
+  float4* ray0;  // o.xyz, d.x
+  float4* ray1;  // d.y, d.z, t_hit, -
+  float4* hit0;  // bits(inst), bits(elem), u, v
+  float4* wgt;   // weight.xyz, -
+  float4* rad;   // radiance.xyz, -
+  float4* bsdf;  // f.xyz, pdf_bsdf   (shade -> probe)
+  float4* alb;   // first-hit albedo
+  float4* nrm;   // first-hit normal
+  float4* med0;  // density.xyz, scanisotropy (only when the scene has volumetric materials)
+  float4* med1;  // scattering.xyz
+  uint4* ctl;    // x = sample, y = draw counter, z = bounce | opbounce << 8 | flags << 16, w = max_roughness bits
+  int* q_ext[2];
+  int* q_shade;  // WF_NKEY segments of n
+  int* q_probe;
+  int* counts;   // WF_C_TOTAL ints
+  int n;         // slots = pixels
+};
+
+JT_DEV unsigned lane_id() { return threadIdx.x & 31u; }
+
+// Warp-aggregated append of `slot` to queue q (counter *cnt) for the lanes with pred set. Must be
+// reached by all 32 lanes of the warp.
+JT_DEV void wf_append(int* q, int* cnt, bool pred, int slot) {
+  unsigned m = __ballot_sync(0xFFFFFFFFu, pred);
+  if (m == 0u) return;
+  int leader = __ffs((int)m) - 1;
+  int base = 0;
+  if ((int)lane_id() == leader) base = atomicAdd(cnt, __popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  if (pred) q[base + __popc(m & ((1u << lane_id()) - 1u))] = slot;
+}
+
+// Same, into one of WF_NKEY queues selected by key (key < 0: no append). All 32 lanes must call.
+JT_DEV void wf_append_keyed(int* q_shade, int* counts, int n, int key, int slot) {
+  unsigned valid = __ballot_sync(0xFFFFFFFFu, key >= 0);
+  if (valid == 0u) return;
+  unsigned peers = __match_any_sync(0xFFFFFFFFu, key);
+  if (key >= 0) {
+    int leader = __ffs((int)peers) - 1;
+    int base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(counts + WF_C_SHADE + key, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    q_shade[(size_t)key * n + base + __popc(peers & ((1u << lane_id()) - 1u))] = slot;
+  }
+}
+
+struct WfPath {  // registers of one slot during a stage
+  unsigned sample, draw;
+  int bounce, opbounce;
+  unsigned flags;
+  float max_roughness;
+};
+JT_DEV WfPath wf_load_ctl(const WfBuffers& B, int s) {
+  uint4 c = B.ctl[s];
+  WfPath p;
+  p.sample = c.x;
+  p.draw = c.y;
+  p.bounce = (int)(c.z & 0xFFu) - 1;
+  p.opbounce = (int)((c.z >> 8) & 0xFFu);
+  p.flags = c.z >> 16;
+  p.max_roughness = __uint_as_float(c.w);
+  return p;
+}
+JT_DEV void wf_store_ctl(const WfBuffers& B, int s, const WfPath& p) {
+  B.ctl[s] = make_uint4(p.sample, p.draw, (unsigned)(p.bounce + 1) | ((unsigned)p.opbounce << 8) | (p.flags << 16),
+                        __float_as_uint(p.max_roughness));
+}
+
+// Start sample `sample` of pixel `s`: RNG draws 0..3, camera ray, unit weight (src/trace.jl:597-608, :286-296).
+JT_DEV void wf_start_sample(const JtDevScene& S, const WfBuffers& B, const DevParams& P, int s, unsigned sample) {
+  Rng rng{jt_rng_key(P.seed, (uint32_t)s, sample), 0u};
+  f2 puv = rng.next2();
+  f2 luv = rng.next2();
+  int i = s % P.width, j = s / P.width;
+  DRay ray = sample_camera(S.cameras[P.camera], i, j, P.width, P.height, puv, luv, P.tentfilter != 0);
+  B.ray0[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
+  B.ray1[s] = make_float4(ray.d.y, ray.d.z, 0.0f, 0.0f);
+  B.wgt[s] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+  B.rad[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  WfPath p;
+  p.sample = sample; p.draw = rng.draw; p.bounce = -1; p.opbounce = 0; p.flags = 0u; p.max_roughness = 0.0f;
+  wf_store_ctl(B, s, p);
+}
+
+// End of trace_sample for slot s (src/trace.jl:625-648); returns true if another sample was started.
+JT_DEV bool wf_finish_sample(const JtDevScene& S, const WfBuffers& B, const DevState& st, const DevParams& P, int s,
+                             const WfPath& p, f3 radiance, int sample_end, unsigned long long* paths_done) {
+  TraceOut r;
+  r.radiance = radiance;
+  r.hit = (p.flags & WF_F_HIT) != 0u;
+  f3 cam_d = f3{0.0f, 0.0f, 0.0f};
+  if (r.hit) {
+    float4 a = B.alb[s], n = B.nrm[s];
+    r.albedo = f3{a.x, a.y, a.z};
+    r.normal = f3{n.x, n.y, n.z};
+  } else {
+    r.albedo = f3{0.0f, 0.0f, 0.0f};
+    r.normal = f3{0.0f, 0.0f, 0.0f};
+    // the camera ray direction (normal AOV of a miss) is a pure function of the RNG stream: recompute
+    Rng rng{jt_rng_key(P.seed, (uint32_t)s, p.sample), 0u};
+    f2 puv = rng.next2();
+    f2 luv = rng.next2();
+    cam_d = sample_camera(S.cameras[P.camera], s % P.width, s / P.width, P.width, P.height, puv, luv, P.tentfilter != 0).d;
+  }
+  accumulate_sample(st, P, S.num_environments != 0, s, (int)p.sample, r, cam_d);
+  (void)paths_done;
+  if ((int)p.sample + 1 < sample_end) {
+    wf_start_sample(S, B, P, s, p.sample + 1u);
+    return true;
+  }
+  return false;
+}
+
+// ---- generate ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wf_generate(JtDevScene S, WfBuffers B, DevParams P, int sample_begin,
+                                                     int sample_end, unsigned long long* counters) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= B.n) return;
+  wf_start_sample(S, B, P, s, (unsigned)sample_begin);
+  B.q_ext[0][s] = s;
+  if (s == 0) {
+    for (int k = 0; k < WF_C_TOTAL; k++) B.counts[k] = 0;
+    B.counts[WF_C_EXT0] = B.n;
+    atomicAdd(counters, (unsigned long long)B.n * (unsigned long long)(sample_end - sample_begin));
+  }
+}
+
+// ---- extend ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128) k_wf_extend(JtDevScene S, WfBuffers B, int cur, unsigned long long* counters) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int count = B.counts[WF_C_EXT0 + cur];
+  int key = -1, s = -1;
+  if (t < count) {
+    s = B.q_ext[cur][t];
+    float4 r0 = B.ray0[s], r1 = B.ray1[s];
+    DRay ray{f3{r0.x, r0.y, r0.z}, f3{r0.w, r1.x, r1.y}, JT_RAY_EPS, INFINITY};
+    DHit h = intersect_scene<MODE>(S, ray);
+    if (h.inst >= 0) {
+      B.hit0[s] = make_float4(__int_as_float(h.inst), __int_as_float(h.elem), h.u, h.v);
+      B.ray1[s] = make_float4(r1.x, r1.y, h.t, 0.0f);
+      key = S.materials[S.instances[h.inst].material].type;
+    } else {
+      B.hit0[s] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.0f, 0.0f);
+      key = WF_KEY_MISS;
+    }
+  }
+  wf_append_keyed(B.q_shade, B.counts, B.n, key, s);
+  unsigned m = __ballot_sync(0xFFFFFFFFu, key >= 0);
+  if (lane_id() == 0u && m) atomicAdd(counters + 1, (unsigned long long)__popc(m));
+}
+
+// Bounce bookkeeping shared by shade (delta / naive / volume-free finishes) and probe:
+// zero / non-finite weight check and Russian roulette (src/trace.jl:455-465).
+// Returns true if the path continues (weight updated in place).
+JT_DEV bool wf_roulette(f3& weight, WfPath& p, uint64_t key) {
+  if (is_zero3(weight) || !finite3(weight)) return false;
+  if (p.bounce > 3) {
+    float rr_prob = jl_min(0.99f, max3(weight));
+    float r = jt_rng_float(key, p.draw++);
+    if (r >= rr_prob) return false;
+    weight = weight * (1.0f / rr_prob);
+  }
+  return true;
+}
+
+// ---- shade ---------------------------------------------------------------------------------------------
+// One thread per queued slot; queues are laid out key after key, each padded to a warp multiple so a
+// warp only ever sees one material type.
+template <int SAMPLER>
+__global__ void __launch_bounds__(128) k_wf_shade(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
+                                                  int sample_end, unsigned long long* counters) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int key = -1, s = -1;
+  {
+    int off = 0;
+#pragma unroll
+    for (int k = 0; k < WF_NKEY; k++) {
+      int c = B.counts[WF_C_SHADE + k];
+      int padded = (c + 31) & ~31;
+      if (key < 0 && t >= off && t < off + padded) {
+        if (t - off < c) {
+          key = k;
+          s = B.q_shade[(size_t)k * B.n + (t - off)];
+        } else {
+          key = -2;  // padding lane
+        }
+      }
+      off += padded;
+    }
+  }
+  bool to_extend = false, to_probe = false;
+  if (s >= 0) {
+    const f3 zero = f3{0.0f, 0.0f, 0.0f};
+    WfPath p = wf_load_ctl(B, s);
+    uint64_t rkey = jt_rng_key(P.seed, (uint32_t)s, p.sample);
+    Rng rng{rkey, p.draw};
+    float4 r0 = B.ray0[s], r1 = B.ray1[s], w4 = B.wgt[s], rad4 = B.rad[s];
+    DRay ray{f3{r0.x, r0.y, r0.z}, f3{r0.w, r1.x, r1.y}, JT_RAY_EPS, INFINITY};
+    f3 weight = f3{w4.x, w4.y, w4.z}, radiance = f3{rad4.x, rad4.y, rad4.z};
+    bool alive = true;
+    p.bounce += 1;  // top of the while loop, src/trace.jl:295-297
+    if (key == WF_KEY_MISS) {
+      if (p.bounce > 0 || !P.envhidden) radiance = radiance + weight * eval_environment(S, ray.d);
+      alive = false;
+    } else {
+      float4 h0 = B.hit0[s];
+      int inst = __float_as_int(h0.x), elem = __float_as_int(h0.y);
+      float hu = h0.z, hv = h0.w, ht = r1.z;
+      bool in_volume = false;
+      float distance = ht;
+      VolPoint medium;
+      medium.density = zero; medium.scattering = zero; medium.scanisotropy = 0.0f;
+      if (SAMPLER == 1 && (p.flags & WF_F_MEDIUM)) {
+        float4 m0 = B.med0[s], m1 = B.med1[s];
+        medium.density = f3{m0.x, m0.y, m0.z};
+        medium.scanisotropy = m0.w;
+        medium.scattering = f3{m1.x, m1.y, m1.z};
+        float q1 = rng.next();
+        float q2 = rng.next();
+        float dist = sample_transmittance(medium.density, ht, q1, q2);
+        weight = (weight * eval_transmittance(medium.density, dist)) / sample_transmittance_pdf(medium.density, dist, ht);
+        in_volume = dist < ht;
+        distance = dist;
+      }
+      f3 outgoing = -ray.d;
+      if (!in_volume) {
+        const JtInstanceRec& I = S.instances[inst];
+        const JtMaterialRec& M = S.materials[I.material];
+        ElemRef E = elem_ref(S, I, elem);
+        f3 position = eval_position(S, I, E, hu, hv);
+        f3 normal = eval_shading_normal(S, I, E, M, hu, hv, outgoing);
+        MatPoint material = eval_material(S, E, M, hu, hv);
+        if (SAMPLER == 1 && P.nocaustics) {
+          p.max_roughness = jl_max(material.roughness, p.max_roughness);
+          material.roughness = p.max_roughness;
+        }
+        bool passthrough = false;
+        if (material.opacity < 1.0f && rng.next() >= material.opacity) {
+          if (p.opbounce > 128) {
+            alive = false;
+          } else {
+            p.opbounce += 1;
+            ray = DRay{position + ray.d * 0.01f, ray.d, JT_RAY_EPS, INFINITY};
+            p.bounce -= 1;  // the `continue` re-enters the loop head, which adds it back
+            to_extend = true;
+          }
+          passthrough = true;
+        }
+        if (!passthrough) {
+          if (p.bounce == 0) {
+            p.flags |= WF_F_HIT;
+            B.alb[s] = make_float4(material.color.x, material.color.y, material.color.z, 0.0f);
+            B.nrm[s] = make_float4(normal.x, normal.y, normal.z, 0.0f);
+          }
+          if (dot3(normal, outgoing) >= 0.0f) radiance = radiance + weight * material.emission;
+          else radiance = radiance + weight * zero;
+          f3 incoming;
+          if (SAMPLER == 1) {
+            if (!is_delta(material)) {
+              if (rng.next() < 0.5f) {
+                float rnl = rng.next();
+                f2 rn = rng.next2();
+                incoming = sample_bsdfcos(material, normal, outgoing, rnl, rn);
+              } else {
+                float rl = rng.next();
+                float rel = rng.next();
+                f2 ruv = rng.next2();
+                incoming = sample_lights(S, position, rl, rel, ruv);
+              }
+              if (is_zero3(incoming)) {
+                alive = false;
+              } else {
+                f3 f = eval_bsdfcos(material, normal, outgoing, incoming);
+                float pb = sample_bsdfcos_pdf(material, normal, outgoing, incoming);
+                B.bsdf[s] = make_float4(f.x, f.y, f.z, pb);
+                to_probe = true;
+              }
+            } else {
+              incoming = sample_delta(material, normal, outgoing, rng.next());
+              weight = (weight * eval_delta(material, normal, outgoing, incoming)) /
+                       sample_delta_pdf(material, normal, outgoing, incoming);
+            }
+            if (alive && is_volumetric_type(M.type) && dot3(normal, outgoing) * dot3(normal, incoming) < 0.0f) {
+              if (!(p.flags & WF_F_MEDIUM)) {
+                B.med0[s] = make_float4(material.density.x, material.density.y, material.density.z, material.scanisotropy);
+                B.med1[s] = make_float4(material.scattering.x, material.scattering.y, material.scattering.z, 0.0f);
+                p.flags |= WF_F_MEDIUM;
+              } else {
+                p.flags &= ~WF_F_MEDIUM;
+              }
+            }
+            if (alive) {
+              ray = DRay{position, incoming, JT_RAY_EPS, INFINITY};
+              if (!to_probe) {  // delta lobe: finish the bounce here
+                p.draw = rng.draw;
+                alive = wf_roulette(weight, p, rkey);
+                rng.draw = p.draw;
+                to_extend = alive;
+              }
+            }
+          } else {  // trace_naive, src/trace.jl:538-571
+            if (material.roughness != 0.0f) {
+              float rnl = rng.next();
+              f2 rn = rng.next2();
+              incoming = sample_bsdfcos(material, normal, outgoing, rnl, rn);
+              if (is_zero3(incoming)) alive = false;
+              else weight = (weight * eval_bsdfcos(material, normal, outgoing, incoming)) /
+                            sample_bsdfcos_pdf(material, normal, outgoing, incoming);
+            } else {
+              incoming = sample_delta(material, normal, outgoing, rng.next());
+              if (is_zero3(incoming)) alive = false;
+              else weight = (weight * eval_delta(material, normal, outgoing, incoming)) /
+                            sample_delta_pdf(material, normal, outgoing, incoming);
+            }
+            if (alive) {
+              p.draw = rng.draw;
+              alive = wf_roulette(weight, p, rkey);
+              rng.draw = p.draw;
+              ray = DRay{position, incoming, JT_RAY_EPS, INFINITY};
+              to_extend = alive;
+            }
+          }
+        }
+      } else {  // scattering event inside the medium, src/trace.jl:423-453
+        f3 position = ray.o + ray.d * distance;
+        f3 incoming;
+        if (rng.next() < 0.5f) {
+          float rnl = rng.next();
+          (void)rnl;
+          f2 rn = rng.next2();
+          incoming = sample_scattering(medium, outgoing, rn);
+        } else {
+          float rl = rng.next();
+          float rel = rng.next();
+          f2 ruv = rng.next2();
+          incoming = sample_lights(S, position, rl, rel, ruv);
+        }
+        if (is_zero3(incoming)) {
+          alive = false;
+        } else {
+          f3 f = eval_scattering(medium, outgoing, incoming);
+          float ps = sample_scattering_pdf(medium, outgoing, incoming);
+          B.bsdf[s] = make_float4(f.x, f.y, f.z, ps);
+          ray = DRay{position, incoming, JT_RAY_EPS, INFINITY};
+          to_probe = true;
+        }
+      }
+    }
+    // the while condition (bounce < bounces) is checked when the next iteration would start
+    if (to_extend && !(p.bounce < P.bounces)) {
+      to_extend = false;
+      alive = false;
+    }
+    p.draw = rng.draw;
+    if (alive) {
+      B.ray0[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
+      B.ray1[s] = make_float4(ray.d.y, ray.d.z, 0.0f, 0.0f);
+      B.wgt[s] = make_float4(weight.x, weight.y, weight.z, 0.0f);
+      B.rad[s] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+      wf_store_ctl(B, s, p);
+    } else {
+      to_probe = false;
+      to_extend = wf_finish_sample(S, B, st, P, s, p, radiance, sample_end, counters);
+    }
+  }
+  wf_append(B.q_probe, B.counts + WF_C_PROBE, to_probe, s);
+  wf_append(B.q_ext[next], B.counts + WF_C_EXT0 + next, to_extend, s);
+}
+
+// ---- probe ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128) k_wf_probe(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
+                                                  int sample_end, unsigned long long* counters) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int count = B.counts[WF_C_PROBE];
+  int s = -1;
+  bool to_extend = false;
+  PathCounters cnt{0u, 0u};
+  if (t < count) {
+    s = B.q_probe[t];
+    WfPath p = wf_load_ctl(B, s);
+    float4 r0 = B.ray0[s], r1 = B.ray1[s], w4 = B.wgt[s], fb = B.bsdf[s];
+    f3 position = f3{r0.x, r0.y, r0.z}, incoming = f3{r0.w, r1.x, r1.y};
+    float pl = sample_lights_pdf<MODE>(S, position, incoming, cnt);
+    f3 weight = (f3{w4.x, w4.y, w4.z} * f3{fb.x, fb.y, fb.z}) / (0.5f * fb.w + 0.5f * pl);
+    uint64_t rkey = jt_rng_key(P.seed, (uint32_t)s, p.sample);
+    bool alive = wf_roulette(weight, p, rkey);
+    if (alive && !(p.bounce < P.bounces)) alive = false;
+    if (alive) {
+      B.wgt[s] = make_float4(weight.x, weight.y, weight.z, 0.0f);
+      wf_store_ctl(B, s, p);
+      to_extend = true;
+    } else {
+      float4 rad4 = B.rad[s];
+      to_extend = wf_finish_sample(S, B, st, P, s, p, f3{rad4.x, rad4.y, rad4.z}, sample_end, counters);
+    }
+  }
+  wf_append(B.q_ext[next], B.counts + WF_C_EXT0 + next, to_extend, s);
+  unsigned lr = __reduce_add_sync(0xFFFFFFFFu, cnt.light_rays);
+  if (lane_id() == 0u && lr) atomicAdd(counters + 2, (unsigned long long)lr);
+}
+
+// ---- advance: recycle the consumed queues for the next iteration -------------------------------------------
+__global__ void k_wf_advance(WfBuffers B, int cur) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    B.counts[WF_C_EXT0 + cur] = 0;
+    B.counts[WF_C_PROBE] = 0;
+    for (int k = 0; k < WF_NKEY; k++) B.counts[WF_C_SHADE + k] = 0;
+  }
+}

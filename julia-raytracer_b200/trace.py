@@ -27,6 +27,7 @@ def to_jt_params(params: Params, accumulate: int = 0) -> A.jt_params:
     p.nocaustics, p.envhidden, p.tentfilter = int(params.nocaustics), int(params.envhidden), int(params.tentfilter)
     p.batch, p.bvhstacksize = params.batch, params.bvhstacksize
     p.traversal = 1 if getattr(params, "gpu_traversal", "wide") == "reference" else 0
+    p.integrator = 1 if getattr(params, "gpu_integrator", "wavefront") == "megakernel" else 0
     p.seed = int(getattr(params, "gpu_seed", 0))
     p.accumulate = accumulate
     return p

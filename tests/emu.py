@@ -28,6 +28,8 @@ def lib():
         L.emu_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
         L.emu_intersect_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
         L.emu_trace_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.emu_trace_wavefront.restype = C.c_int
+        L.emu_trace_wavefront.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
         _LIB = L
     return _LIB
 
@@ -63,15 +65,17 @@ class Emu:
         self.L.emu_intersect_instance(self.h, rays.ctypes.data, instances.ctypes.data, len(rays), traversal, hits.ctypes.data)
         return hits
 
-    def trace(self, params, width, height, begin, end):
+    def trace(self, params, width, height, begin, end, wavefront=False):
         n = width * height
         image = np.zeros((n, 4), np.float32)
         albedo = np.zeros((n, 4), np.float32)
         normal = np.zeros((n, 4), np.float32)
         hits = np.zeros(n, np.int32)
         cnt = np.zeros(2, np.uint64)
-        self.L.emu_trace_range(self.h, C.byref(params), width, height, begin, end, image.ctypes.data,
-                               albedo.ctypes.data, normal.ctypes.data, hits.ctypes.data, cnt.ctypes.data)
+        cnt = np.zeros(3, np.uint64)
+        fn = self.L.emu_trace_wavefront if wavefront else self.L.emu_trace_range
+        fn(self.h, C.byref(params), width, height, begin, end, image.ctypes.data,
+           albedo.ctypes.data, normal.ctypes.data, hits.ctypes.data, cnt.ctypes.data)
         return dict(image=image.reshape(height, width, 4), albedo=albedo.reshape(height, width, 4)[..., :3],
                     normal=normal.reshape(height, width, 4)[..., :3], hits=hits.reshape(height, width).astype(np.int64),
                     scene_rays=int(cnt[0]), light_rays=int(cnt[1]))

@@ -2,6 +2,7 @@
 #include "emu_shims.h"
 #define JT_DEV static inline
 #include "../../julia-raytracer_b200/csrc/jt_dev_trace.cuh"
+#include "../../julia-raytracer_b200/csrc/jt_dev_wavefront.cuh"
 
 #include <omp.h>
 #include <vector>
@@ -104,5 +105,54 @@ EMU_API void emu_trace_range(void* h, const jt_params* p, int width, int height,
       }
     }
   if (counters) { counters[0] += scene_rays; counters[1] += light_rays; }
+}
+
+// The wavefront integrator stepped sequentially (one emulated thread = one single-lane warp).
+EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int height, int begin, int end, float* image,
+                                float* albedo, float* normal, int* hits, uint64_t* counters) {
+  Emu* e = (Emu*)h;
+  DevParams P;
+  P.camera = p->camera - 1; P.width = width; P.height = height; P.bounces = p->bounces; P.sampler = p->sampler;
+  P.clamp = p->clamp; P.nocaustics = p->nocaustics; P.envhidden = p->envhidden; P.tentfilter = p->tentfilter;
+  P.accumulate = p->accumulate; P.seed = p->seed;
+  DevState st{(float4*)image, (float4*)albedo, (float4*)normal, hits};
+  int n = width * height;
+  std::vector<float4> f4[10];
+  for (auto& v : f4) v.assign(n, float4{0, 0, 0, 0});
+  std::vector<uint4> ctl(n);
+  std::vector<int> q0(n), q1(n), qs((size_t)n * WF_NKEY), qp(n), counts(WF_C_TOTAL, 0);
+  WfBuffers B;
+  B.ray0 = f4[0].data(); B.ray1 = f4[1].data(); B.hit0 = f4[2].data(); B.wgt = f4[3].data(); B.rad = f4[4].data();
+  B.bsdf = f4[5].data(); B.alb = f4[6].data(); B.nrm = f4[7].data(); B.med0 = f4[8].data(); B.med1 = f4[9].data();
+  B.ctl = ctl.data(); B.q_ext[0] = q0.data(); B.q_ext[1] = q1.data(); B.q_shade = qs.data(); B.q_probe = qp.data();
+  B.counts = counts.data(); B.n = n;
+  unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto run = [&](int threads, auto&& kernel) {
+    for (int t = 0; t < threads; t++) { emu_blockIdx.x = (unsigned)t; kernel(); }
+  };
+  run(n, [&] { k_wf_generate(e->dev, B, P, begin, end, cnt); });
+  int cur = 0, iterations = 0;
+  while (counts[WF_C_EXT0 + cur] > 0) {
+    int next = cur ^ 1;
+    int ne = counts[WF_C_EXT0 + cur];
+    if (p->traversal == 1) run(ne, [&] { k_wf_extend<MODE_REF>(e->dev, B, cur, cnt); });
+    else run(ne, [&] { k_wf_extend<MODE_WIDE>(e->dev, B, cur, cnt); });
+    int ns = 0;
+    for (int k = 0; k < WF_NKEY; k++) ns += (counts[WF_C_SHADE + k] + 31) & ~31;
+    if (P.sampler == 1) {
+      run(ns, [&] { k_wf_shade<1>(e->dev, B, st, P, next, end, cnt); });
+      int np = counts[WF_C_PROBE];
+      if (p->traversal == 1) run(np, [&] { k_wf_probe<MODE_REF>(e->dev, B, st, P, next, end, cnt); });
+      else run(np, [&] { k_wf_probe<MODE_WIDE>(e->dev, B, st, P, next, end, cnt); });
+    } else {
+      run(ns, [&] { k_wf_shade<2>(e->dev, B, st, P, next, end, cnt); });
+    }
+    emu_blockIdx.x = 0;
+    k_wf_advance(B, cur);
+    cur = next;
+    iterations++;
+  }
+  if (counters) { counters[0] += cnt[1]; counters[1] += cnt[2]; counters[2] += cnt[0]; }
+  return iterations;
 }
 }

@@ -17,3 +17,24 @@ static inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); re
 static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+
+// ---- single-lane "warps" so that the wavefront kernels (ballot / match_any / shuffle queue appends)
+// can be stepped slot by slot on the host: every emulated thread is its own warp of one lane.
+struct emu_dim { unsigned x, y, z; };
+static thread_local emu_dim emu_threadIdx = {0, 0, 0}, emu_blockIdx = {0, 0, 0}, emu_blockDim = {1, 1, 1};
+#define threadIdx emu_threadIdx
+#define blockIdx emu_blockIdx
+#define blockDim emu_blockDim
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline unsigned __match_any_sync(unsigned, int) { return 1u; }
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int) { return v; }
+static inline unsigned __reduce_add_sync(unsigned, unsigned v) { return v; }
+static inline int atomicAdd(int* p, int v) { int o = *p; *p += v; return o; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+#ifndef __global__
+#define __global__
+#endif

@@ -65,13 +65,14 @@ CASES = [("cornellbox", 2, {}), ("cornellbox", 1, {}), ("features1", 1, {}), ("f
 
 @pytest.mark.parametrize("name,sampler,extra", CASES)
 @pytest.mark.parametrize("traversal", [1, 0])
-def test_fixed_sample_set_images(pair, name, sampler, extra, traversal):
+@pytest.mark.parametrize("wavefront", [False, True])
+def test_fixed_sample_set_images(pair, name, sampler, extra, traversal, wavefront):
     o, e = pair(name)
     p = orc.make_params(resolution=64, samples=3, batch=3, sampler=sampler, traversal=traversal, seed=11, **extra)
     w, h = o.make_state(p)
     o.trace_samples(p)
     ref = o.get_state()
-    got = e.trace(p, w, h, 0, 3)
+    got = e.trace(p, w, h, 0, 3, wavefront=wavefront)
     c = o.counters(reset=True)
     img = got["image"] * np.float32(1.0 / 3.0) if extra.get("accumulate") else got["image"]
     if traversal == 1:

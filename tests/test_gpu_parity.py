@@ -103,8 +103,10 @@ def test_fixed_sample_set_images(pair, name, sampler, extra):
     o.trace_samples(op)
     ref = o.get_state()
     oc = o.counters(reset=True)
-    for traversal in ("reference", "wide"):
-        p = _params(resolution=res, sampler=sampler, gpu_seed=31, gpu_traversal=traversal, **extra)
+    for traversal, integrator in (("reference", "wavefront"), ("wide", "wavefront"), ("reference", "megakernel"),
+                                  ("wide", "megakernel")):
+        p = _params(resolution=res, sampler=sampler, gpu_seed=31, gpu_traversal=traversal, gpu_integrator=integrator,
+                    **extra)
         st = trace.make_trace_state(d, p)
         assert (st.width, st.height) == (w, h)
         d.counters(reset=True)
@@ -114,7 +116,7 @@ def test_fixed_sample_set_images(pair, name, sampler, extra):
         img = st.image.reshape(h, w, 4)
         err = np.abs(img - ref["image"]).max(axis=-1)
         if traversal == "reference":
-            assert np.array_equal(img, ref["image"]), float(err.max())
+            assert np.array_equal(img, ref["image"]), (integrator, float(err.max()))
             assert np.array_equal(st.albedo.reshape(h, w, 3), ref["albedo"])
             assert np.array_equal(st.normal.reshape(h, w, 3), ref["normal"])
             assert np.array_equal(st.hits.reshape(h, w), ref["hits"])
