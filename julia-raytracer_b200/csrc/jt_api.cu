@@ -60,6 +60,7 @@ struct jt_scene {
   int num_cameras = 0, num_instances = 0;
   unsigned long long* d_counters = nullptr;  // [0] camera paths [1] scene rays [2] light rays
   uint64_t launches = 0;
+  unsigned persist_blocks = 0;
   jt_scene_stats stats;
   int64_t device_bytes = 0;
 };
@@ -236,6 +237,38 @@ __global__ void __launch_bounds__(128) k_intersect(JtDevScene S, const jt_ray* _
   jt_ray r = rays[i];
   DRay ray{f3{r.o[0], r.o[1], r.o[2]}, f3{r.d[0], r.d[1], r.d[2]}, r.tmin, r.tmax};
   store_hit(out + i, intersect_scene<MODE>(S, ray));
+}
+
+// Wide-BVH closest hit with persistent warps + dynamic fetch (jt_dev_persist.cuh).
+__global__ void __launch_bounds__(JT_PERSIST_BLOCK) k_intersect_persist(JtDevScene S, const jt_ray* __restrict__ rays,
+                                                                        long long n, HitOut* __restrict__ out,
+                                                                        int* fetch_counter) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int count = (int)n;
+  uint2 stack[JT_WIDE_STACK];
+  PersistLane L;
+  bool live = false, more = true;
+  int s = -1;
+  for (;;) {
+    __syncwarp();
+    if (s >= 0 && !live) {
+      store_hit(out + s, DHit{L.best.t, L.best.u, L.best.v, L.best.inst, L.best.elem});
+      s = -1;
+    }
+    if (more) {
+      bool want = !live;
+      int idx = persist_fetch(fetch_counter, want, count);
+      if (idx >= 0) {
+        s = idx;
+        jt_ray r = rays[idx];
+        persist_init(L, S, f3{r.o[0], r.o[1], r.o[2]}, f3{r.d[0], r.d[1], r.d[2]}, r.tmin, r.tmax, S.wide_root, -1);
+        live = S.wide_root >= 0;
+      }
+      if (__ballot_sync(FULL, want && idx < 0)) more = false;
+    }
+    if (__ballot_sync(FULL, live || s >= 0) == 0u) break;
+    persist_traverse(S, L, stack, live, more);
+  }
 }
 
 template <int MODE>
@@ -456,6 +489,18 @@ extern "C" int jt_state_download(jt_state* st, float* image, float* albedo, floa
 // =================================================================================================
 // the hot path
 // =================================================================================================
+__global__ void k_wf_extend_persist(JtDevScene, WfBuffers, int, unsigned long long*);
+// Persistent kernels: one resident wave of blocks (SM count x occupancy), each warp loops over the queue.
+static unsigned persist_grid(jt_scene* sc) {
+  if (sc->persist_blocks == 0) {
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wf_extend_persist, JT_PERSIST_BLOCK, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device);
+    sc->persist_blocks = (unsigned)std::max(1, per_sm) * (unsigned)std::max(1, sms);
+  }
+  return sc->persist_blocks;
+}
+
 static DevParams dev_params(const jt_params* p, const jt_state* st) {
   DevParams P;
   P.camera = p->camera - 1;
@@ -466,6 +511,8 @@ static DevParams dev_params(const jt_params* p, const jt_state* st) {
   P.seed = p->seed;
   return P;
 }
+
+static unsigned persist_grid(jt_scene* sc);
 
 static int wf_prepare(jt_scene* sc, jt_state* st) {
   if (st->wf_ready) return JT_OK;
@@ -513,7 +560,12 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
     // shrink, because every slot appears at most once per iteration)
     unsigned ge = (unsigned)((remaining + 127) / 128), gs = (unsigned)((remaining + 32 * WF_NKEY + 127) / 128);
     (void)g_ext; (void)g_shade;
-    k_wf_extend<MODE><<<ge, 128, 0, q>>>(sc->dev, B, cur, sc->d_counters);
+    if (MODE == MODE_WIDE) {
+      unsigned gp = std::min<unsigned>((unsigned)((remaining + JT_PERSIST_BLOCK - 1) / JT_PERSIST_BLOCK), persist_grid(sc));
+      k_wf_extend_persist<<<gp, JT_PERSIST_BLOCK, 0, q>>>(sc->dev, B, cur, sc->d_counters);
+    } else {
+      k_wf_extend<MODE><<<ge, 128, 0, q>>>(sc->dev, B, cur, sc->d_counters);
+    }
     if (P.sampler == 1) {
       k_wf_shade<1><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
       k_wf_probe<MODE><<<ge, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
@@ -601,7 +653,7 @@ extern "C" int jt_elapsed_ms(jt_scene* sc, float* ms) {
 // =================================================================================================
 extern "C" int jt_intersect_device(jt_scene* sc, const void* d_rays, int64_t n, int traversal, void* d_hits) {
   if (!sc || (n > 0 && (!d_rays || !d_hits)) || n < 0) return jt_set_error(JT_ERR_INVALID, "jt_intersect_device: bad argument");
-  if (traversal != 0 && traversal != 1) return jt_set_error(JT_ERR_INVALID, "traversal must be 0 or 1");
+  if (traversal < 0 || traversal > 2) return jt_set_error(JT_ERR_INVALID, "traversal must be 0, 1 or 2");
   if (n == 0) return JT_OK;
   JT_CUDA(cudaSetDevice(sc->device));
   unsigned blocks = (unsigned)((n + 127) / 128);
@@ -609,8 +661,17 @@ extern "C" int jt_intersect_device(jt_scene* sc, const void* d_rays, int64_t n, 
     JT_CUDA(cudaEventRecord(sc->ev_start, sc->stream));
     sc->timing_open = true;
   }
-  if (traversal == 1) k_intersect<MODE_REF><<<blocks, 128, 0, sc->stream>>>(sc->dev, (const jt_ray*)d_rays, n, (HitOut*)d_hits);
-  else k_intersect<MODE_WIDE><<<blocks, 128, 0, sc->stream>>>(sc->dev, (const jt_ray*)d_rays, n, (HitOut*)d_hits);
+  if (traversal == 1) {
+    k_intersect<MODE_REF><<<blocks, 128, 0, sc->stream>>>(sc->dev, (const jt_ray*)d_rays, n, (HitOut*)d_hits);
+  } else if (traversal == 2) {  // plain one-thread-per-ray wide walk (kept for A/B measurements)
+    k_intersect<MODE_WIDE><<<blocks, 128, 0, sc->stream>>>(sc->dev, (const jt_ray*)d_rays, n, (HitOut*)d_hits);
+  } else {
+    if (n > 0x7FFFFFFF) return jt_set_error(JT_ERR_INVALID, "jt_intersect_device: more than 2^31-1 rays per call");
+    int* fetch = (int*)(sc->d_counters + 7);
+    JT_CUDA(cudaMemsetAsync(fetch, 0, 4, sc->stream));
+    unsigned pblocks = std::min<unsigned>((unsigned)((n + JT_PERSIST_BLOCK - 1) / JT_PERSIST_BLOCK), persist_grid(sc));
+    k_intersect_persist<<<pblocks, JT_PERSIST_BLOCK, 0, sc->stream>>>(sc->dev, (const jt_ray*)d_rays, n, (HitOut*)d_hits, fetch);
+  }
   sc->launches++;
   JT_CUDA(cudaGetLastError());
   JT_CUDA(cudaEventRecord(sc->ev_stop, sc->stream));

@@ -17,6 +17,13 @@
 
 enum { MODE_WIDE = 0, MODE_REF = 1 };
 
+// work counters, compiled in only by the host emulation of tests/emu (never in the CUDA build)
+#ifdef JT_EMU_COUNT
+#define JT_COUNT(name) (++jt_emu_counts.name)
+#else
+#define JT_COUNT(name) ((void)0)
+#endif
+
 // ---- exact leaf test --------------------------------------------------------------------------
 // intersect_triangle (src/geometry.jl:206-236) on a record that stores p1, p2-p1, p3-p1.
 // Returns true and (t,u,v) when the reference's test accepts against [tmin, tmax].
@@ -180,7 +187,7 @@ JT_DEV DHit ref_scene(const JtDevScene& S, const DRay& ray) {
 // ===============================================================================================
 // MODE_WIDE
 // ===============================================================================================
-#define JT_WIDE_STACK 40
+#define JT_WIDE_STACK 64 /* entries; staging rejects scenes whose wide BVH could need more */
 
 struct WideRay {  // per-space traversal constants
   f3 o, d;
@@ -206,11 +213,17 @@ JT_DEV void wide_ray_setup(WideRay& R, f3 o, f3 d) {
 }
 
 JT_DEV uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
+// byte i of w as a float without an I2F: splice the byte into the mantissa of 2^23 (one PRMT), then
+// subtract 2^23 (exact). I2F runs at 1/8 of the FP32 rate; the node test needs 48 conversions.
+JT_DEV float byte_to_float(uint32_t w, int i) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t)i)) - 8388608.0f;
+}
 
 // Slab-test the 8 children of one node. Returns the 32-bit hit word: bits 24..31 internal
 // children in priority order, bits 0..23 triangle records.
 JT_DEV uint32_t wide_node_hits(const float4* __restrict__ wnodes, uint32_t node, const WideRay& R, float tmin,
                                float tmax, uint2* ngroup_out, uint2* tgroup_out) {
+  JT_COUNT(wide_nodes);
   const float4* np = wnodes + 5 * (size_t)node;
   float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
   uint32_t eimask = __float_as_uint(n0.w);
@@ -243,9 +256,9 @@ JT_DEV uint32_t wide_node_hits(const float4* __restrict__ wnodes, uint32_t node,
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       uint32_t meta = byte_of(meta_w[h], j);
-      float t0x = fmaf((float)byte_of(nearx, j), sx, alx), t1x = fmaf((float)byte_of(farx, j), sx, ahx);
-      float t0y = fmaf((float)byte_of(neary, j), sy, aly), t1y = fmaf((float)byte_of(fary, j), sy, ahy);
-      float t0z = fmaf((float)byte_of(nearz, j), sz, alz), t1z = fmaf((float)byte_of(farz, j), sz, ahz);
+      float t0x = fmaf(byte_to_float(nearx, j), sx, alx), t1x = fmaf(byte_to_float(farx, j), sx, ahx);
+      float t0y = fmaf(byte_to_float(neary, j), sy, aly), t1y = fmaf(byte_to_float(fary, j), sy, ahy);
+      float t0z = fmaf(byte_to_float(nearz, j), sz, alz), t1z = fmaf(byte_to_float(farz, j), sz, ahz);
       float lo = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
       float hi = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
       if (meta != 0u && lo <= hi) {
@@ -320,7 +333,9 @@ JT_DEV void wide_walk(const JtDevScene& S, uint32_t root, f3 o, f3 d, float tmin
       const float4* tp = S.wtris + 3 * (size_t)wtri;
       float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
       uint32_t flags = __float_as_uint(r2.w);
+      JT_COUNT(wide_prims);
       if (flags & 0x100u) {
+        JT_COUNT(wide_instances);
         // instance record: park the rest of the world-level work, switch to instance space
         int inst = __float_as_int(r1.w);
         if (tgroup.y != 0u) stack[sp++] = tgroup;

@@ -18,6 +18,7 @@
 // no atomics on the image. Queue appends are warp-aggregated: one atomicAdd per warp per queue,
 // lane offsets from ballot / match_any masks.
 #pragma once
+#include "jt_dev_persist.cuh"
 #include "jt_dev_trace.cuh"
 
 #define WF_NKEY 9     /* material types 0..7 + miss */
@@ -26,6 +27,7 @@
 #define WF_C_EXT0 0
 #define WF_C_EXT1 1
 #define WF_C_PROBE 2
+#define WF_C_FETCH 3 /* next unfetched index of the extend queue (persistent extend kernel) */
 #define WF_C_SHADE 4  /* .. WF_C_SHADE + WF_NKEY */
 #define WF_C_TOTAL 16
 
@@ -185,6 +187,54 @@ __global__ void __launch_bounds__(128) k_wf_extend(JtDevScene S, WfBuffers B, in
   wf_append_keyed(B.q_shade, B.counts, B.n, key, s);
   unsigned m = __ballot_sync(0xFFFFFFFFu, key >= 0);
   if (lane_id() == 0u && m) atomicAdd(counters + 1, (unsigned long long)__popc(m));
+}
+
+// Persistent-warp extend over the wide BVH (jt_dev_persist.cuh): lanes refill from the queue as they finish.
+__global__ void __launch_bounds__(JT_PERSIST_BLOCK) k_wf_extend_persist(JtDevScene S, WfBuffers B, int cur,
+                                                                        unsigned long long* counters) {
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int count = B.counts[WF_C_EXT0 + cur];
+  const int* queue = B.q_ext[cur];
+  uint2 stack[JT_WIDE_STACK];
+  PersistLane L;
+  bool live = false, more = true;
+  int s = -1;
+  unsigned nrays = 0u;
+  for (;;) {
+    __syncwarp();
+    int key = -1;
+    if (s >= 0 && !live) {  // retire a finished ray: hit record + material-sorted shading queue
+      float4 r1 = B.ray1[s];
+      if (L.best.inst >= 0) {
+        B.hit0[s] = make_float4(__int_as_float(L.best.inst), __int_as_float(L.best.elem), L.best.u, L.best.v);
+        B.ray1[s] = make_float4(r1.x, r1.y, L.best.t, 0.0f);
+        key = S.materials[S.instances[L.best.inst].material].type;
+      } else {
+        B.hit0[s] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.0f, 0.0f);
+        key = WF_KEY_MISS;
+      }
+      nrays++;
+    }
+    wf_append_keyed(B.q_shade, B.counts, B.n, key, s);
+    if (!live) s = -1;
+    if (more) {
+      bool want = !live;
+      int idx = persist_fetch(B.counts + WF_C_FETCH, want, count);
+      if (idx >= 0) {
+        s = queue[idx];
+        float4 r0 = B.ray0[s], r1 = B.ray1[s];
+        persist_init(L, S, f3{r0.x, r0.y, r0.z}, f3{r0.w, r1.x, r1.y}, JT_RAY_EPS, INFINITY, S.wide_root, -1);
+        live = S.wide_root >= 0;
+        if (!live) L.best.inst = -1;
+      }
+      if (__ballot_sync(FULL, want && idx < 0)) more = false;
+    }
+    unsigned pending = __ballot_sync(FULL, live || s >= 0);
+    if (pending == 0u) break;
+    persist_traverse(S, L, stack, live, more);
+  }
+  unsigned total = __reduce_add_sync(FULL, nrays);
+  if (lane_id() == 0u && total) atomicAdd(counters + 1, (unsigned long long)total);
 }
 
 // Bounce bookkeeping shared by shade (delta / naive / volume-free finishes) and probe:
@@ -443,6 +493,7 @@ __global__ void k_wf_advance(WfBuffers B, int cur) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     B.counts[WF_C_EXT0 + cur] = 0;
     B.counts[WF_C_PROBE] = 0;
+    B.counts[WF_C_FETCH] = 0;
     for (int k = 0; k < WF_NKEY; k++) B.counts[WF_C_SHADE + k] = 0;
   }
 }

@@ -8,7 +8,7 @@
 #include "jt_internal.h"
 
 #ifndef JT_WIDE_STACK
-#define JT_WIDE_STACK 40
+#define JT_WIDE_STACK 64
 #endif
 
 static inline float4 mk_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
@@ -218,7 +218,8 @@ int jt_stage_scene(const jt_scene_desc* d, JtStagedScene* S) {
     shape_recs[s].wide_root = wide.shape_root[s];
     blas_depth = std::max(blas_depth, max_wide_depth(wide.nodes, wide.shape_root[s]));
   }
-  if (depth + blas_depth + 4 > JT_WIDE_STACK)
+  // per level at most one deferred node group + one postponed triangle group (jt_dev_persist.cuh)
+  if (2 * (depth + blas_depth) + 4 > JT_WIDE_STACK)
     return jt_set_error(JT_ERR_UNSUPPORTED, "wide BVH too deep for the traversal stack (%d + %d levels, limit %d)",
                         depth, blas_depth, JT_WIDE_STACK - 4);
   for (int o = 0; o < 8; o++) tri_rank.insert(tri_rank.end(), wide.tri_rank[o].begin(), wide.tri_rank[o].end());

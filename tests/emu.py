@@ -30,6 +30,7 @@ def lib():
         L.emu_trace_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.emu_trace_wavefront.restype = C.c_int
         L.emu_trace_wavefront.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
+        L.emu_wide_counts.argtypes = [C.c_void_p, C.c_int]
         _LIB = L
     return _LIB
 
@@ -79,3 +80,9 @@ class Emu:
         return dict(image=image.reshape(height, width, 4), albedo=albedo.reshape(height, width, 4)[..., :3],
                     normal=normal.reshape(height, width, 4)[..., :3], hits=hits.reshape(height, width).astype(np.int64),
                     scene_rays=int(cnt[0]), light_rays=int(cnt[1]))
+
+
+def wide_counts(reset=True):
+    out = np.zeros(3, np.uint64)
+    lib().emu_wide_counts(out.ctypes.data, int(reset))
+    return dict(nodes=int(out[0]), prims=int(out[1]), instances=int(out[2]))

@@ -57,12 +57,22 @@ static void put_hit(jt_hit* o, const DHit& h) {
   }
 }
 
+static unsigned long long g_wide_counts[3] = {0, 0, 0};
+EMU_API void emu_wide_counts(unsigned long long* out, int reset) {
+  for (int k = 0; k < 3; k++) { out[k] = g_wide_counts[k]; if (reset) g_wide_counts[k] = 0; }
+}
 EMU_API void emu_intersect(void* h, const jt_ray* rays, int64_t n, int traversal, jt_hit* out) {
   Emu* e = (Emu*)h;
-#pragma omp parallel for schedule(dynamic, 1024)
-  for (int64_t i = 0; i < n; i++) {
-    DRay r{f3{rays[i].o[0], rays[i].o[1], rays[i].o[2]}, f3{rays[i].d[0], rays[i].d[1], rays[i].d[2]}, rays[i].tmin, rays[i].tmax};
-    put_hit(out + i, traversal == 1 ? intersect_scene<MODE_REF>(e->dev, r) : intersect_scene<MODE_WIDE>(e->dev, r));
+#pragma omp parallel
+  {
+    jt_emu_counts = jt_emu_counts_t{0, 0, 0};
+#pragma omp for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < n; i++) {
+      DRay r{f3{rays[i].o[0], rays[i].o[1], rays[i].o[2]}, f3{rays[i].d[0], rays[i].d[1], rays[i].d[2]}, rays[i].tmin, rays[i].tmax};
+      put_hit(out + i, traversal == 1 ? intersect_scene<MODE_REF>(e->dev, r) : intersect_scene<MODE_WIDE>(e->dev, r));
+    }
+#pragma omp critical
+    { g_wide_counts[0] += jt_emu_counts.wide_nodes; g_wide_counts[1] += jt_emu_counts.wide_prims; g_wide_counts[2] += jt_emu_counts.wide_instances; }
   }
 }
 EMU_API void emu_intersect_instance(void* h, const jt_ray* rays, const int64_t* inst, int64_t n, int traversal, jt_hit* out) {

@@ -38,3 +38,16 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 #ifndef __global__
 #define __global__
 #endif
+
+#define JT_EMU_COUNT 1
+struct jt_emu_counts_t { unsigned long long wide_nodes, wide_prims, wide_instances; };
+static thread_local jt_emu_counts_t jt_emu_counts = {0, 0, 0};
+
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
+  unsigned long long v = ((unsigned long long)y << 32) | x;
+  unsigned r = 0;
+  for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xFFu) << (8 * i);
+  return r;
+}
+static inline void __syncwarp(unsigned = 0xFFFFFFFFu) {}
+#define JT_FETCH_THRESHOLD 1 /* single-lane warps */
