@@ -215,9 +215,11 @@ def main():
     w, h = state.width, state.height
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
+    shard = importlib.import_module("julia-raytracer_b200.shard")
+
     def step(k):
-        begin = (k * world + rank) * spp
-        trace.trace_sample_range(state, dscene, params, begin, begin + spp)
+        begin, end = shard.step_range(k, world, rank, spp)
+        trace.trace_sample_range(state, dscene, params, begin, end)
 
     def barrier():
         dscene.synchronize()
@@ -244,7 +246,7 @@ def main():
     bufs = state.device_buffers()
     if world > 1:  # the single end-of-job merge of the accumulation buffers (NCCL reduce over NVLink)
         img = torch.as_tensor(_DevBuf(bufs["image"], bufs["count"] * 4), device="cuda")
-        dist.reduce(img, dst=0, op=dist.ReduceOp.SUM)
+        shard.reduce_sums(img, dst=0)
     barrier()
     wall_s = time.perf_counter() - t0
     clk = clocks.stop()

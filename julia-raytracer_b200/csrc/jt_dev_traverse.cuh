@@ -213,10 +213,11 @@ JT_DEV void wide_ray_setup(WideRay& R, f3 o, f3 d) {
 }
 
 JT_DEV uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
-// byte i of w as a float without an I2F: splice the byte into the mantissa of 2^23 (one PRMT), then
-// subtract 2^23 (exact). I2F runs at 1/8 of the FP32 rate; the node test needs 48 conversions.
-JT_DEV float byte_to_float(uint32_t w, int i) {
-  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t)i)) - 8388608.0f;
+// Byte i of w as the float 256 + b/128 without an I2F (1/8 of the FP32 rate; the node test needs 48
+// conversions): one PRMT splices the byte into mantissa bits 8..15 of 256.0f. The affine map back to b is
+// folded into the slab FMA: t = b*s + a = (256 + b/128)*(128 s) + (a - 32768 s).
+JT_DEV float byte_as_biased_float(uint32_t w, int i) {
+  return __uint_as_float(__byte_perm(w, 0x43800000u, 0x7604u | ((uint32_t)i << 4)));
 }
 
 // Slab-test the 8 children of one node. Returns the 32-bit hit word: bits 24..31 internal
@@ -233,11 +234,18 @@ JT_DEV uint32_t wide_node_hits(const float4* __restrict__ wnodes, uint32_t node,
   float sy = __uint_as_float(((eimask >> 8) & 0xFFu) << 23) * R.idy;
   float sz = __uint_as_float(((eimask >> 16) & 0xFFu) << 23) * R.idz;
   float ax = (n0.x - R.o.x) * R.idx, ay = (n0.y - R.o.y) * R.idy, az = (n0.z - R.o.z) * R.idz;
+  // slack: 2^-21 of the magnitudes involved + 2^-7 of a grid step for the biased-byte folding below
   const float k = 4.76837158e-7f;  // 2^-21
-  float ex = k * fmaf(256.0f, fabsf(sx), fabsf(ax));
-  float ey = k * fmaf(256.0f, fabsf(sy), fabsf(ay));
-  float ez = k * fmaf(256.0f, fabsf(sz), fabsf(az));
-  float alx = ax - ex, ahx = ax + ex, aly = ay - ey, ahy = ay + ey, alz = az - ez, ahz = az + ez;
+  float ex = fmaf(k, fmaf(256.0f, fabsf(sx), fabsf(ax)), 0.0078125f * fabsf(sx));
+  float ey = fmaf(k, fmaf(256.0f, fabsf(sy), fabsf(ay)), 0.0078125f * fabsf(sy));
+  float ez = fmaf(k, fmaf(256.0f, fabsf(sz), fabsf(az)), 0.0078125f * fabsf(sz));
+  // fold the byte bias: b = 128 f - 32768
+  float alx = fmaf(-32768.0f, sx, ax) - ex, ahx = fmaf(-32768.0f, sx, ax) + ex;
+  float aly = fmaf(-32768.0f, sy, ay) - ey, ahy = fmaf(-32768.0f, sy, ay) + ey;
+  float alz = fmaf(-32768.0f, sz, az) - ez, ahz = fmaf(-32768.0f, sz, az) + ez;
+  sx *= 128.0f;
+  sy *= 128.0f;
+  sz *= 128.0f;
   uint32_t imask = eimask >> 24;
   uint32_t meta_w[2] = {__float_as_uint(n1.z), __float_as_uint(n1.w)};
   uint32_t qlox[2] = {__float_as_uint(n2.x), __float_as_uint(n2.y)};
@@ -256,9 +264,9 @@ JT_DEV uint32_t wide_node_hits(const float4* __restrict__ wnodes, uint32_t node,
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       uint32_t meta = byte_of(meta_w[h], j);
-      float t0x = fmaf(byte_to_float(nearx, j), sx, alx), t1x = fmaf(byte_to_float(farx, j), sx, ahx);
-      float t0y = fmaf(byte_to_float(neary, j), sy, aly), t1y = fmaf(byte_to_float(fary, j), sy, ahy);
-      float t0z = fmaf(byte_to_float(nearz, j), sz, alz), t1z = fmaf(byte_to_float(farz, j), sz, ahz);
+      float t0x = fmaf(byte_as_biased_float(nearx, j), sx, alx), t1x = fmaf(byte_as_biased_float(farx, j), sx, ahx);
+      float t0y = fmaf(byte_as_biased_float(neary, j), sy, aly), t1y = fmaf(byte_as_biased_float(fary, j), sy, ahy);
+      float t0z = fmaf(byte_as_biased_float(nearz, j), sz, alz), t1z = fmaf(byte_as_biased_float(farz, j), sz, ahz);
       float lo = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
       float hi = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
       if (meta != 0u && lo <= hi) {
