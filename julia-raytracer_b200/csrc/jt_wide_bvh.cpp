@@ -232,6 +232,116 @@ class Collapser {
     return r.rank;
   }
 
+  // ---- binned-SAH binary tree over record indices (the fast mode's own topology) -------------------------
+  // The reference tree (centroid middle split, src/bvh.jl:185-216) only defines tie-break ranks; which boxes
+  // a ray visits is free, so the wide BVH is collapsed from a surface-area-heuristic tree instead:
+  // 16 bins per axis, leaves of <= 3 records (the per-slot limit of the wide node).
+  int sah_tree(std::vector<int>& recs, size_t a, size_t b, Tree& t) {
+    size_t n = b - a;
+    if (n == 0) return -1;
+    Box3 box, cbox;
+    box.reset();
+    cbox.reset();
+    for (size_t i = a; i < b; i++) {
+      const Box3& rb = t.recs[(size_t)recs[i]].box;
+      box.add(rb);
+      float c[3] = {0.5f * (rb.lo[0] + rb.hi[0]), 0.5f * (rb.lo[1] + rb.hi[1]), 0.5f * (rb.lo[2] + rb.hi[2])};
+      cbox.add(c);
+    }
+    auto make_leaf = [&]() {
+      BNode leaf;
+      leaf.box = box;
+      leaf.first = (int)leaf_store_.size();
+      leaf.count = (int)n;
+      for (size_t i = a; i < b; i++) leaf_store_.push_back(recs[i]);
+      t.nodes.push_back(leaf);
+      return (int)t.nodes.size() - 1;
+    };
+    if (n == 1) return make_leaf();
+    const int NB = 16;
+    int best_axis = -1, best_bin = -1;
+    float best_cost = std::numeric_limits<float>::infinity();
+    for (int ax = 0; ax < 3; ax++) {
+      float lo = cbox.lo[ax], ext = cbox.hi[ax] - cbox.lo[ax];
+      if (!(ext > 0.0f)) continue;
+      Box3 bins[NB];
+      int cnt[NB];
+      for (int k = 0; k < NB; k++) {
+        bins[k].reset();
+        cnt[k] = 0;
+      }
+      float scale = (float)NB / ext;
+      for (size_t i = a; i < b; i++) {
+        const Box3& rb = t.recs[(size_t)recs[i]].box;
+        int k = (int)((0.5f * (rb.lo[ax] + rb.hi[ax]) - lo) * scale);
+        k = std::max(0, std::min(NB - 1, k));
+        bins[k].add(rb);
+        cnt[k]++;
+      }
+      float right_area[NB];
+      int right_cnt[NB];
+      Box3 acc;
+      acc.reset();
+      int c = 0;
+      for (int k = NB - 1; k > 0; k--) {
+        acc.add(bins[k]);
+        c += cnt[k];
+        right_area[k] = acc.area();
+        right_cnt[k] = c;
+      }
+      acc.reset();
+      c = 0;
+      for (int k = 0; k < NB - 1; k++) {
+        acc.add(bins[k]);
+        c += cnt[k];
+        if (c == 0 || right_cnt[k + 1] == 0) continue;
+        // wide-node aware cost: a slot holds up to 3 records, so count ceil(n/3) leaf slots per side
+        float cost = acc.area() * (float)((c + 2) / 3) + right_area[k + 1] * (float)((right_cnt[k + 1] + 2) / 3);
+        if (cost < best_cost) {
+          best_cost = cost;
+          best_axis = ax;
+          best_bin = k;
+        }
+      }
+    }
+    if (n <= 3) {
+      // keep small groups together unless splitting clearly pays (leaf cost = 1 slot of the node box)
+      float leaf_cost = box.area();
+      if (best_axis < 0 || best_cost >= leaf_cost) return make_leaf();
+    }
+    size_t m;
+    if (best_axis < 0) {
+      m = a + n / 2;  // identical centroids: split the list
+    } else {
+      float lo = cbox.lo[best_axis], scale = (float)NB / (cbox.hi[best_axis] - cbox.lo[best_axis]);
+      auto mid = std::partition(recs.begin() + (long)a, recs.begin() + (long)b, [&](int r) {
+        const Box3& rb = t.recs[(size_t)r].box;
+        int k = (int)((0.5f * (rb.lo[best_axis] + rb.hi[best_axis]) - lo) * scale);
+        k = std::max(0, std::min(NB - 1, k));
+        return k <= best_bin;
+      });
+      m = (size_t)(mid - recs.begin());
+      if (m == a || m == b) m = a + n / 2;
+    }
+    int l = sah_tree(recs, a, m, t);
+    int r = sah_tree(recs, m, b, t);
+    BNode in;
+    in.left = l;
+    in.right = r;
+    in.box = t.nodes[(size_t)l].box;
+    in.box.add(t.nodes[(size_t)r].box);
+    t.nodes.push_back(in);
+    return (int)t.nodes.size() - 1;
+  }
+
+  // all records of a shape (reference element order), optionally with a baked instance id
+  void shape_records(int shape_id, int inst, std::vector<int>* recs, Tree& t) {
+    const JtHostShape& s = shapes_[(size_t)shape_id];
+    if (s.kind == 0 || s.ref_nodes.empty() || s.num_elements() == 0) return;
+    const std::vector<uint32_t>* erank = shape_rank(shape_id);
+    for (int64_t e = 0; e < s.num_elements(); e++) element_records(s, e, inst, erank, recs, t);
+  }
+
   // ---- emit a wide BVH from a binary tree; returns the root index in out_->nodes ---------------------------
   int emit(const Tree& t, int root) {
     if (root < 0) return -1;
@@ -385,71 +495,58 @@ class Collapser {
     for (size_t s = 0; s < shapes_.size(); s++) {
       Tree t;
       leaf_store_.clear();
-      int root = shape_tree((int)s, -1, t);
+      std::vector<int> recs;
+      shape_records((int)s, -1, &recs, t);
+      int root = sah_tree(recs, 0, recs.size(), t);
       out_->shape_root[s] = emit(t, root);
     }
-    // top level: TLAS tree with identity-frame instances spliced in
+    // top level: ONE surface-area tree over every triangle of the identity-frame instances (inlined: the
+    // two-level structure is pure overhead for them) plus one reference record per
+    // remaining instance. Order follows the reference TLAS only through the rank tables.
     visit_ranks(tlas_nodes, tlas_prims, (int64_t)insts_.size(), out_->inst_rank);
     Tree t;
     leaf_store_.clear();
-    std::function<int(int64_t)> conv = [&](int64_t ni) -> int {
-      const jt_bvh_node& n = tlas_nodes[(size_t)ni];
-      if (n.internal) {
-        int l = conv(n.start - 1);
-        int r = conv(n.start);
-        if (l < 0) return r;
-        if (r < 0) return l;
-        BNode in;
-        in.left = l;
-        in.right = r;
-        in.box = t.nodes[(size_t)l].box;
-        in.box.add(t.nodes[(size_t)r].box);
-        t.nodes.push_back(in);
-        return (int)t.nodes.size() - 1;
-      }
-      std::vector<Item> items;
-      for (int64_t i = n.start - 1; i < n.start - 1 + n.num; i++) {
-        int inst = (int)(tlas_prims[(size_t)i] - 1);
-        const JtHostInstance& I = insts_[(size_t)inst];
-        const JtHostShape& s = shapes_[(size_t)I.shape];
-        if (s.kind == 0 || s.ref_nodes.empty() || s.num_elements() == 0) continue;
-        if (I.inlined) {
-          int sub = shape_tree(I.shape, inst, t);
-          if (sub >= 0) items.push_back(Item{sub, -1});
-          out_->inlined_instances++;
-        } else {
-          // instance-reference record; box = transform_bbox(frame, BLAS root box) (src/geometry.jl:70-86)
-          const jt_bvh_node& rootn = s.ref_nodes[0];
-          Rec r;
-          r.box.reset();
-          for (int c = 0; c < 8; c++) {
-            float p[3] = {(c & 4) ? rootn.bbox_max[0] : rootn.bbox_min[0],
-                          (c & 2) ? rootn.bbox_max[1] : rootn.bbox_min[1],
-                          (c & 1) ? rootn.bbox_max[2] : rootn.bbox_min[2]};
-            float w[3];
-            for (int k = 0; k < 3; k++)
-              w[k] = ((I.frame[k] * p[0] + I.frame[3 + k] * p[1]) + I.frame[6 + k] * p[2]) + I.frame[9 + k];
-            r.box.add(w);
-          }
-          // a hair of slack: the BLAS is tested in instance space, not against this box
-          for (int k = 0; k < 3; k++) {
-            float pad = 1e-5f * std::max(std::fabs(r.box.lo[k]), std::fabs(r.box.hi[k])) + 1e-30f;
-            r.box.lo[k] -= pad;
-            r.box.hi[k] += pad;
-          }
-          memset(&r.tri, 0, sizeof(r.tri));
-          r.tri.element = -1;
-          r.tri.instance = inst;
-          r.tri.flags = 1u << 8;
-          for (int o = 0; o < 8; o++) r.rank[o] = 0;
-          items.push_back(Item{-1, (int)t.recs.size()});
-          t.recs.push_back(r);
-          out_->instanced_instances++;
+    std::vector<int> top;
+    std::vector<char> in_tlas(insts_.size(), 0);
+    for (int64_t p : tlas_prims) in_tlas[(size_t)(p - 1)] = 1;
+    for (size_t inst = 0; inst < insts_.size(); inst++) {
+      if (!in_tlas[inst]) continue;
+      const JtHostInstance& I = insts_[inst];
+      const JtHostShape& s = shapes_[(size_t)I.shape];
+      if (s.kind == 0 || s.ref_nodes.empty() || s.num_elements() == 0) continue;
+      if (I.inlined) {
+        shape_records(I.shape, (int)inst, &top, t);
+        out_->inlined_instances++;
+      } else {
+        // instance-reference record; box = transform_bbox(frame, BLAS root box) (src/geometry.jl:70-86)
+        const jt_bvh_node& rootn = s.ref_nodes[0];
+        Rec r;
+        r.box.reset();
+        for (int c = 0; c < 8; c++) {
+          float p[3] = {(c & 4) ? rootn.bbox_max[0] : rootn.bbox_min[0], (c & 2) ? rootn.bbox_max[1] : rootn.bbox_min[1],
+                        (c & 1) ? rootn.bbox_max[2] : rootn.bbox_min[2]};
+          float w[3];
+          for (int k = 0; k < 3; k++)
+            w[k] = ((I.frame[k] * p[0] + I.frame[3 + k] * p[1]) + I.frame[6 + k] * p[2]) + I.frame[9 + k];
+          r.box.add(w);
         }
+        // a hair of slack: the BLAS is tested in instance space, not against this box
+        for (int k = 0; k < 3; k++) {
+          float pad = 1e-5f * std::max(std::fabs(r.box.lo[k]), std::fabs(r.box.hi[k])) + 1e-30f;
+          r.box.lo[k] -= pad;
+          r.box.hi[k] += pad;
+        }
+        memset(&r.tri, 0, sizeof(r.tri));
+        r.tri.element = -1;
+        r.tri.instance = (int)inst;
+        r.tri.flags = 1u << 8;
+        for (int o = 0; o < 8; o++) r.rank[o] = 0;
+        top.push_back((int)t.recs.size());
+        t.recs.push_back(r);
+        out_->instanced_instances++;
       }
-      return tree_over(items, 0, items.size(), t);
-    };
-    int root = tlas_nodes.empty() ? -1 : conv(0);
+    }
+    int root = sah_tree(top, 0, top.size(), t);
     out_->top_root = emit(t, root);
     return JT_OK;
   }
