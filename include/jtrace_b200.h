@@ -205,7 +205,9 @@ JT_API int jt_state_set_samples(jt_state* state, int32_t samples);
 
 /* ---- the hot path --------------------------------------------------------------------------- */
 /* trace_samples (src/trace.jl:215-274): advances state.samples by params.batch (clamped to
- * params.samples). Asynchronous: returns after enqueueing; nothing is copied back. */
+ * params.samples). Lazily batched: the reference calls this samples/batch times with batch = 1 by default,
+ * so contiguous requests are merged and launched in chunks (32 samples) or at the next synchronisation
+ * point (download, jt_synchronize, counters, device_buffers). Nothing is copied back. */
 JT_API int jt_trace_samples(jt_scene* scene, jt_state* state, const jt_params* params);
 /* Same loop body for an explicit range of global sample indices [begin, end): the unit that
  * is sharded across GPUs. Does not touch state.samples bookkeeping beyond adding end-begin. */

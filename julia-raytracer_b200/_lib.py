@@ -10,7 +10,7 @@ import os
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjtrace_b200.so")
+LIB_PATH = os.environ.get("JTRACE_B200_LIB") or os.path.join(_HERE, "libjtrace_b200.so")  # override: tuning variants
 
 # every symbol include/jtrace_b200.h declares
 EXPORTS = [

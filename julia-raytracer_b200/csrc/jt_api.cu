@@ -61,6 +61,7 @@ struct jt_scene {
   unsigned long long* d_counters = nullptr;  // [0] camera paths [1] scene rays [2] light rays
   uint64_t launches = 0;
   unsigned persist_blocks = 0;
+  std::vector<jt_state*> states;  // for flushing lazily batched sample ranges
   jt_scene_stats stats;
   int64_t device_bytes = 0;
 };
@@ -79,7 +80,22 @@ struct jt_state {
   void* d_pack = nullptr;
   void* h_pack = nullptr;
   uint64_t wf_iterations = 0;
+  // lazily batched work: trace_samples is called samples/batch times (batch defaults to 1, src/cli.jl:78-81);
+  // contiguous requests are merged and launched in chunks of JT_LAZY_SPP samples or at the next sync point
+  bool has_pending = false;
+  int pending_begin = 0, pending_end = 0;
+  jt_params pending_params;
 };
+
+#define JT_LAZY_SPP 32
+static int flush_state(jt_state* st);
+static int flush_scene(jt_scene* sc) {
+  for (jt_state* st : sc->states) {
+    int rc = flush_state(st);
+    if (rc) return rc;
+  }
+  return JT_OK;
+}
 
 template <class T>
 static int upload(jt_scene* sc, const std::vector<T>& v, const T** out) {
@@ -96,6 +112,7 @@ static int upload(jt_scene* sc, const std::vector<T>& v, const T** out) {
 
 extern "C" void jt_scene_destroy(jt_scene* sc) {
   if (!sc) return;
+  for (jt_state* st : sc->states) st->has_pending = false;
   cudaSetDevice(sc->device);
   for (void* p : sc->allocs) cudaFree(p);
   if (sc->ev_start) cudaEventDestroy(sc->ev_start);
@@ -194,6 +211,8 @@ extern "C" int jt_scene_get_stats(jt_scene* sc, jt_scene_stats* out) {
 extern "C" int jt_scene_counters(jt_scene* sc, jt_counters* out, int reset) {
   if (!sc || !out) return jt_set_error(JT_ERR_INVALID, "jt_scene_counters: null argument");
   JT_CUDA(cudaSetDevice(sc->device));
+  int frc = flush_scene(sc);
+  if (frc) return frc;
   JT_CUDA(cudaStreamSynchronize(sc->stream));
   unsigned long long h[8];
   JT_CUDA(cudaMemcpy(h, sc->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
@@ -399,6 +418,7 @@ extern "C" int jt_state_create(jt_scene* sc, const jt_params* p, jt_state** out)
     return jt_set_error(JT_ERR_CUDA, "cudaMalloc of the trace state failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   st->dev.image = (float4*)a; st->dev.albedo = (float4*)b; st->dev.normal = (float4*)c; st->dev.hits = (int*)d;
+  sc->states.push_back(st);
   *out = st;
   return jt_state_reset(st);
 }
@@ -406,6 +426,7 @@ extern "C" int jt_state_create(jt_scene* sc, const jt_params* p, jt_state** out)
 extern "C" int jt_state_reset(jt_state* st) {
   if (!st) return jt_set_error(JT_ERR_INVALID, "jt_state_reset: null argument");
   jt_scene* sc = st->scene;
+  st->has_pending = false;
   JT_CUDA(cudaSetDevice(sc->device));
   size_t n = (size_t)st->width * st->height;
   JT_CUDA(cudaMemsetAsync(st->dev.image, 0, n * 16, sc->stream));
@@ -418,6 +439,13 @@ extern "C" int jt_state_reset(jt_state* st) {
 
 extern "C" void jt_state_destroy(jt_state* st) {
   if (!st) return;
+  st->has_pending = false;
+  auto& v = st->scene->states;
+  for (size_t i = 0; i < v.size(); i++)
+    if (v[i] == st) {
+      v.erase(v.begin() + (long)i);
+      break;
+    }
   cudaSetDevice(st->scene->device);
   cudaStreamSynchronize(st->scene->stream);
   cudaFree(st->dev.image); cudaFree(st->dev.albedo); cudaFree(st->dev.normal); cudaFree(st->dev.hits);
@@ -445,6 +473,8 @@ extern "C" int jt_state_set_samples(jt_state* st, int32_t samples) {
 extern "C" int jt_state_device_buffers(jt_state* st, void** image, void** albedo, void** normal, void** hits,
                                        int64_t* count) {
   if (!st) return jt_set_error(JT_ERR_INVALID, "jt_state_device_buffers: null argument");
+  int frc = flush_state(st);
+  if (frc) return frc;
   if (image) *image = st->dev.image;
   if (albedo) *albedo = st->dev.albedo;
   if (normal) *normal = st->dev.normal;
@@ -457,6 +487,8 @@ extern "C" int jt_state_download(jt_state* st, float* image, float* albedo, floa
   if (!st) return jt_set_error(JT_ERR_INVALID, "jt_state_download: null argument");
   jt_scene* sc = st->scene;
   JT_CUDA(cudaSetDevice(sc->device));
+  int frc = flush_state(st);
+  if (frc) return frc;
   long long n = (long long)st->width * st->height;
   // persistent staging: one packed device buffer + one pinned host buffer (48 B per pixel)
   if (!st->d_pack) JT_CUDA(cudaMalloc(&st->d_pack, (size_t)n * 48));
@@ -609,15 +641,40 @@ static int launch_range(jt_scene* sc, jt_state* st, const jt_params* p, int begi
   return JT_OK;
 }
 
+static int flush_state(jt_state* st) {
+  if (!st->has_pending) return JT_OK;
+  st->has_pending = false;
+  jt_scene* sc = st->scene;
+  JT_CUDA(cudaSetDevice(sc->device));
+  return launch_range(sc, st, &st->pending_params, st->pending_begin, st->pending_end);
+}
+
+static bool same_render_params(const jt_params& a, const jt_params& b) {
+  return a.camera == b.camera && a.resolution == b.resolution && a.bounces == b.bounces && a.sampler == b.sampler &&
+         a.clamp == b.clamp && a.nocaustics == b.nocaustics && a.envhidden == b.envhidden &&
+         a.tentfilter == b.tentfilter && a.traversal == b.traversal && a.seed == b.seed &&
+         a.accumulate == b.accumulate && a.integrator == b.integrator;
+}
+
 extern "C" int jt_trace_sample_range(jt_scene* sc, jt_state* st, const jt_params* p, int32_t begin, int32_t end) {
   if (!sc || !st || st->scene != sc) return jt_set_error(JT_ERR_INVALID, "jt_trace_sample_range: bad scene/state");
   int rc = check_params(sc, p);
   if (rc) return rc;
   if (begin < 0 || end < begin) return jt_set_error(JT_ERR_INVALID, "bad sample range [%d, %d)", begin, end);
-  JT_CUDA(cudaSetDevice(sc->device));
-  rc = launch_range(sc, st, p, begin, end);
-  if (rc) return rc;
+  if (end == begin) return JT_OK;
+  if (st->has_pending && (begin != st->pending_end || !same_render_params(*p, st->pending_params))) {
+    if ((rc = flush_state(st))) return rc;
+  }
+  if (st->has_pending) {
+    st->pending_end = end;
+  } else {
+    st->has_pending = true;
+    st->pending_begin = begin;
+    st->pending_end = end;
+    st->pending_params = *p;
+  }
   st->samples += end - begin;
+  if (st->pending_end - st->pending_begin >= JT_LAZY_SPP) return flush_state(st);
   return JT_OK;
 }
 
@@ -633,6 +690,8 @@ extern "C" int jt_trace_samples(jt_scene* sc, jt_state* st, const jt_params* p) 
 extern "C" int jt_synchronize(jt_scene* sc) {
   if (!sc) return jt_set_error(JT_ERR_INVALID, "jt_synchronize: null argument");
   JT_CUDA(cudaSetDevice(sc->device));
+  int frc = flush_scene(sc);
+  if (frc) return frc;
   JT_CUDA(cudaStreamSynchronize(sc->stream));
   return JT_OK;
 }
@@ -641,6 +700,8 @@ extern "C" int jt_elapsed_ms(jt_scene* sc, float* ms) {
   if (!sc || !ms) return jt_set_error(JT_ERR_INVALID, "jt_elapsed_ms: null argument");
   JT_CUDA(cudaSetDevice(sc->device));
   *ms = 0.0f;
+  int frc = flush_scene(sc);
+  if (frc) return frc;
   if (!sc->timing_open) return JT_OK;
   JT_CUDA(cudaEventSynchronize(sc->ev_stop));
   JT_CUDA(cudaEventElapsedTime(ms, sc->ev_start, sc->ev_stop));

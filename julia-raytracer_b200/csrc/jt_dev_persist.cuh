@@ -6,7 +6,7 @@
 //   * rays of one warp need very different numbers of steps -> persistent warps that REFILL idle
 //     lanes from the ray queue whenever fewer than JT_FETCH_THRESHOLD lanes are still traversing;
 //   * node steps and triangle tests interleave differently per lane -> every loop iteration is one
-//     node step for all lanes that have one, and triangle tests run only when at least 1/5 of the
+//     node step for all lanes that have one, and triangle tests run only when at least 1/4 of the
 //     live lanes hold triangles (others postpone theirs onto the traversal stack).
 // The loop is warp-uniform (all 32 lanes iterate together, idle lanes predicated off) so every
 // ballot is full-mask. Results are identical to wide_walk(): the closest hit and its tie-break do
@@ -70,7 +70,10 @@ JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, uint2* stack, 
       }
     }
     // ---- B: triangle tests, only while enough lanes have some ----------------------------------------
-    const int quorum = __popc(am) / 5;
+#ifndef JT_TRI_QUORUM_DIV
+#define JT_TRI_QUORUM_DIV 4
+#endif
+    const int quorum = __popc(am) / JT_TRI_QUORUM_DIV;
     const int threshold = quorum > 1 ? quorum : 1;
     for (;;) {
       bool has = live && L.tgroup.y != 0u;

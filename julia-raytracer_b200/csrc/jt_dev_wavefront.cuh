@@ -190,7 +190,10 @@ __global__ void __launch_bounds__(128) k_wf_extend(JtDevScene S, WfBuffers B, in
 }
 
 // Persistent-warp extend over the wide BVH (jt_dev_persist.cuh): lanes refill from the queue as they finish.
-__global__ void __launch_bounds__(JT_PERSIST_BLOCK) k_wf_extend_persist(JtDevScene S, WfBuffers B, int cur,
+#ifndef JT_EXTEND_MINBLOCKS
+#define JT_EXTEND_MINBLOCKS 7
+#endif
+__global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_extend_persist(JtDevScene S, WfBuffers B, int cur,
                                                                         unsigned long long* counters) {
   const unsigned FULL = 0xFFFFFFFFu;
   const int count = B.counts[WF_C_EXT0 + cur];
@@ -254,8 +257,14 @@ JT_DEV bool wf_roulette(f3& weight, WfPath& p, uint64_t key) {
 // ---- shade ---------------------------------------------------------------------------------------------
 // One thread per queued slot; queues are laid out key after key, each padded to a warp multiple so a
 // warp only ever sees one material type.
+#ifndef JT_SHADE_MINBLOCKS
+#define JT_SHADE_MINBLOCKS 6 /* tuned on B200: profiles/r01/tuning_variants.txt */
+#endif
+#ifndef JT_PROBE_MINBLOCKS
+#define JT_PROBE_MINBLOCKS 6
+#endif
 template <int SAMPLER>
-__global__ void __launch_bounds__(128) k_wf_shade(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
+__global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
                                                   int sample_end, unsigned long long* counters) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int key = -1, s = -1;
@@ -457,7 +466,7 @@ __global__ void __launch_bounds__(128) k_wf_shade(JtDevScene S, WfBuffers B, Dev
 
 // ---- probe ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(128) k_wf_probe(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
+__global__ void __launch_bounds__(128, JT_PROBE_MINBLOCKS) k_wf_probe(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
                                                   int sample_end, unsigned long long* counters) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int count = B.counts[WF_C_PROBE];
