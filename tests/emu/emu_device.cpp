@@ -2,6 +2,7 @@
 #include "emu_shims.h"
 #define JT_DEV static inline
 #include "../../julia-raytracer_b200/csrc/jt_dev_trace.cuh"
+#include "../../julia-raytracer_b200/csrc/jt_dev_persist.cuh"
 #include "../../julia-raytracer_b200/csrc/jt_dev_wavefront.cuh"
 
 #include <omp.h>
@@ -57,6 +58,15 @@ static void put_hit(jt_hit* o, const DHit& h) {
   }
 }
 
+// the persistent-warp traversal state machine (jt_dev_persist.cuh), one single-lane "warp" per ray
+static DHit persist_one(const JtDevScene& S, const DRay& r) {
+  uint2 stack[JT_WIDE_STACK], tstack[JT_TRI_STACK];
+  PersistLane L;
+  persist_init(L, S, r.o, r.d, r.tmin, r.tmax, S.wide_root, -1);
+  bool live = S.wide_root >= 0;
+  persist_traverse(S, L, stack, tstack, live, false);
+  return DHit{L.best.t, L.best.u, L.best.v, L.best.inst, L.best.elem};
+}
 static unsigned long long g_wide_counts[3] = {0, 0, 0};
 EMU_API void emu_wide_counts(unsigned long long* out, int reset) {
   for (int k = 0; k < 3; k++) { out[k] = g_wide_counts[k]; if (reset) g_wide_counts[k] = 0; }
@@ -69,7 +79,8 @@ EMU_API void emu_intersect(void* h, const jt_ray* rays, int64_t n, int traversal
 #pragma omp for schedule(dynamic, 1024)
     for (int64_t i = 0; i < n; i++) {
       DRay r{f3{rays[i].o[0], rays[i].o[1], rays[i].o[2]}, f3{rays[i].d[0], rays[i].d[1], rays[i].d[2]}, rays[i].tmin, rays[i].tmax};
-      put_hit(out + i, traversal == 1 ? intersect_scene<MODE_REF>(e->dev, r) : intersect_scene<MODE_WIDE>(e->dev, r));
+      put_hit(out + i, traversal == 1 ? intersect_scene<MODE_REF>(e->dev, r)
+                                      : (traversal == 3 ? persist_one(e->dev, r) : intersect_scene<MODE_WIDE>(e->dev, r)));
     }
 #pragma omp critical
     { g_wide_counts[0] += jt_emu_counts.wide_nodes; g_wide_counts[1] += jt_emu_counts.wide_prims; g_wide_counts[2] += jt_emu_counts.wide_instances; }

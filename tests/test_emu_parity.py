@@ -26,7 +26,7 @@ def pair(scenes):
 
 
 @pytest.mark.parametrize("name", SCENES)
-@pytest.mark.parametrize("traversal", [1, 0])
+@pytest.mark.parametrize("traversal", [1, 0, 3])  # 3 = the persistent-warp state machine, single-lane
 def test_identical_rays(pair, name, traversal):
     o, e = pair(name)
     p = orc.make_params(resolution=128)
