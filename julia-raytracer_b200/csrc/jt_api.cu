@@ -265,7 +265,6 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK) k_intersect_persist(JtDevSce
   const unsigned FULL = 0xFFFFFFFFu;
   const int count = (int)n;
   uint2 stack[JT_WIDE_STACK];
-  uint2 tstack[JT_TRI_STACK];
   PersistLane L;
   bool live = false, more = true;
   int s = -1;
@@ -287,7 +286,7 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK) k_intersect_persist(JtDevSce
       if (__ballot_sync(FULL, want && idx < 0)) more = false;
     }
     if (__ballot_sync(FULL, live || s >= 0) == 0u) break;
-    persist_traverse(S, L, stack, tstack, live, more);
+    persist_traverse(S, L, stack, live, more);
   }
 }
 

@@ -6,8 +6,8 @@
 //   * rays of one warp need very different numbers of steps -> persistent warps that REFILL idle
 //     lanes from the ray queue whenever fewer than JT_FETCH_THRESHOLD lanes are still traversing;
 //   * node steps and triangle tests interleave differently per lane -> every loop iteration is one
-//     node step for all lanes that have one; found triangle groups go to a per-lane pending stack and
-//     are tested in warp-wide triangle phases in which EVERY lane with pending triangles takes part.
+//     node step for all lanes that have one, and triangle tests run only when at least 1/4 of the
+//     live lanes hold triangles (others postpone theirs onto the traversal stack).
 // The loop is warp-uniform (all 32 lanes iterate together, idle lanes predicated off) so every
 // ballot is full-mask. Results are identical to wide_walk(): the closest hit and its tie-break do
 // not depend on the order in which candidates are tested.
@@ -19,14 +19,10 @@
 #endif
 #define JT_PERSIST_BLOCK 128
 
-#define JT_TRI_STACK 8
-
 struct PersistLane {
   WideRay R;            // current space (world or instance)
-  uint2 ngroup;         // node group in hand
-  int sp, blas_sp;      // node stack height; height at BLAS entry (-1 = world space)
-  int tsp, blas_tsp;    // pending-triangle stack height; height at BLAS entry
-  int cur_inst;
+  uint2 ngroup, tgroup;
+  int sp, blas_sp, cur_inst;
   WideBest best;
   float best_t, tmin;
   uint32_t world_oct;
@@ -40,10 +36,9 @@ JT_DEV void persist_init(PersistLane& L, const JtDevScene& S, f3 o, f3 d, float 
   L.wd = d;
   L.world_oct = L.R.rank_oct;
   L.ngroup = make_uint2((uint32_t)root, 0x80000000u);
+  L.tgroup = make_uint2(0u, 0u);
   L.sp = 0;
   L.blas_sp = -1;
-  L.tsp = 0;
-  L.blas_tsp = 0;
   L.cur_inst = single_inst;
   L.best = WideBest{0.0f, 0.0f, 0.0f, -1, -1, -1};
   L.best_t = tmax;
@@ -52,69 +47,55 @@ JT_DEV void persist_init(PersistLane& L, const JtDevScene& S, f3 o, f3 d, float 
 
 // One warp-uniform traversal episode: runs until every lane has finished its ray or (when `more` rays
 // are waiting) fewer than JT_FETCH_THRESHOLD lanes remain live. `live` is updated per lane.
-//
-// Per iteration: (A) every lane with a node group takes ONE node step; the triangle group it finds goes
-// onto the lane's pending-triangle stack. (B) triangle phase: all lanes with pending triangles test one
-// triangle per inner iteration -- entered when a quorum of lanes has some, or when a lane can make no other
-// progress (no node work left in its current space, or its pending stack is full). (C) lanes without a node
-// group pop the node stack, leave their BLAS, or finish.
-// Pending triangles are stratified: BLAS-space groups are always above world-space ones and are flushed
-// before the lane leaves the BLAS, so the top of the stack is always in the lane's current space.
-JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, uint2* stack, uint2* tstack, bool& live, bool more) {
+JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, uint2* stack, bool& live, bool more) {
   const unsigned FULL = 0xFFFFFFFFu;
   for (;;) {
     unsigned am = __ballot_sync(FULL, live);
     if (am == 0u) break;
     if (more && __popc(am) < JT_FETCH_THRESHOLD) break;
     // ---- A: one node step -------------------------------------------------------------------------
-    if (live && L.ngroup.y > 0x00FFFFFFu) {
-      uint32_t hits = L.ngroup.y;
-      uint32_t bit = 31u - (uint32_t)__clz(hits);
-      hits &= ~(1u << bit);
-      L.ngroup.y = hits;
-      if (hits > 0x00FFFFFFu) stack[L.sp++] = L.ngroup;
-      uint32_t slot = (bit - 24u) ^ L.R.oct;
-      uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
-      uint2 tg;
-      wide_node_hits(S.wnodes, L.ngroup.x + rel, L.R, L.tmin, L.best_t, &L.ngroup, &tg);
-      if (tg.y != 0u) tstack[L.tsp++] = tg;
+    if (live) {
+      if (L.ngroup.y > 0x00FFFFFFu) {
+        uint32_t hits = L.ngroup.y;
+        uint32_t bit = 31u - (uint32_t)__clz(hits);
+        hits &= ~(1u << bit);
+        L.ngroup.y = hits;
+        if (hits > 0x00FFFFFFu) stack[L.sp++] = L.ngroup;
+        uint32_t slot = (bit - 24u) ^ L.R.oct;
+        uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
+        wide_node_hits(S.wnodes, L.ngroup.x + rel, L.R, L.tmin, L.best_t, &L.ngroup, &L.tgroup);
+      } else {
+        L.tgroup = L.ngroup;  // the popped entry was a (postponed) triangle group
+        L.ngroup = make_uint2(0u, 0u);
+      }
     }
-    // ---- B: triangle phase ----------------------------------------------------------------------------
+    // ---- B: triangle tests, only while enough lanes have some ----------------------------------------
 #ifndef JT_TRI_QUORUM_DIV
 #define JT_TRI_QUORUM_DIV 4
 #endif
-    const int quorum_hi = __popc(am) / JT_TRI_QUORUM_DIV > 1 ? __popc(am) / JT_TRI_QUORUM_DIV : 1;
-    const int quorum_lo = quorum_hi / 2 > 1 ? quorum_hi / 2 : 1;
-    bool first = true;
+    const int quorum = __popc(am) / JT_TRI_QUORUM_DIV;
+    const int threshold = quorum > 1 ? quorum : 1;
     for (;;) {
-      const int node_base = L.blas_sp >= 0 ? L.blas_sp : 0;
-      const int tri_base = L.blas_sp >= 0 ? L.blas_tsp : 0;
-      bool want = live && L.tsp > tri_base;
-      bool must = want && ((L.ngroup.y <= 0x00FFFFFFu && L.sp == node_base) || L.tsp >= JT_TRI_STACK);
-      unsigned wm = __ballot_sync(FULL, want);
-      if (wm == 0u) break;
-      unsigned mm = __ballot_sync(FULL, must);
-      if (mm == 0u && __popc(wm) < (first ? quorum_hi : quorum_lo)) break;
-      first = false;
-      if (want) {
-        uint2 tg = tstack[L.tsp - 1];
-        uint32_t bit = (uint32_t)__ffs((int)tg.y) - 1u;
-        tg.y &= ~(1u << bit);
-        if (tg.y != 0u) tstack[L.tsp - 1] = tg;
-        else L.tsp--;
-        uint32_t wtri = tg.x + bit;
+      bool has = live && L.tgroup.y != 0u;
+      unsigned tm = __ballot_sync(FULL, has);
+      if (tm == 0u || __popc(tm) < threshold) break;
+      if (has) {
+        uint32_t bit = (uint32_t)__ffs((int)L.tgroup.y) - 1u;
+        L.tgroup.y &= ~(1u << bit);
+        uint32_t wtri = L.tgroup.x + bit;
         const float4* tp = S.wtris + 3 * (size_t)wtri;
         float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
         uint32_t flags = __float_as_uint(r2.w);
-        if (flags & 0x100u) {  // instance record (world space only): park the node group, enter the BLAS
+        if (flags & 0x100u) {  // instance record: park world-level work, enter the BLAS
           int inst = __float_as_int(r1.w);
+          if (L.tgroup.y != 0u) stack[L.sp++] = L.tgroup;
           if (L.ngroup.y > 0x00FFFFFFu) stack[L.sp++] = L.ngroup;
           L.blas_sp = L.sp;
-          L.blas_tsp = L.tsp;
           L.cur_inst = inst;
           const JtInstanceRec& I = S.instances[inst];
           wide_ray_setup(L.R, xform_point(I.inv, L.wo), xform_vector(I.inv, L.wd));
           L.ngroup = make_uint2((uint32_t)S.shapes[I.shape].wide_root, 0x80000000u);
+          L.tgroup = make_uint2(0u, 0u);
         } else {
           float t, u, v;
           if (tri_test(L.R.o, L.R.d, L.tmin, L.best_t, f3{r0.x, r0.y, r0.z}, f3{r1.x, r1.y, r1.z},
@@ -130,21 +111,20 @@ JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, uint2* stack, 
         }
       }
     }
-    // ---- C: pop the next node group, leave the BLAS, or finish ---------------------------------------------
-    if (live && L.ngroup.y <= 0x00FFFFFFu) {
-      const int node_base = L.blas_sp >= 0 ? L.blas_sp : 0;
-      const int tri_base = L.blas_sp >= 0 ? L.blas_tsp : 0;
-      if (L.sp > node_base) {
-        L.ngroup = stack[--L.sp];
-      } else if (L.tsp > tri_base) {
-        // pending triangles of this space remain: the next triangle phase is forced (`must`)
-      } else if (L.blas_sp >= 0) {
-        L.blas_sp = -1;
-        L.cur_inst = -1;
-        wide_ray_setup(L.R, L.wo, L.wd);
-        if (L.sp > 0) L.ngroup = stack[--L.sp];
-      } else {
-        live = false;
+    // ---- C: postpone leftovers, pop the next group, leave the BLAS, or finish ---------------------------
+    if (live) {
+      if (L.tgroup.y != 0u) {
+        stack[L.sp++] = L.tgroup;
+        L.tgroup = make_uint2(0u, 0u);
+      }
+      if (L.ngroup.y <= 0x00FFFFFFu) {
+        if (L.sp == L.blas_sp) {
+          L.blas_sp = -1;
+          L.cur_inst = -1;
+          wide_ray_setup(L.R, L.wo, L.wd);
+        }
+        if (L.sp == 0) live = false;
+        else L.ngroup = stack[--L.sp];
       }
     }
   }

@@ -199,7 +199,6 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
   const int count = B.counts[WF_C_EXT0 + cur];
   const int* queue = B.q_ext[cur];
   uint2 stack[JT_WIDE_STACK];
-  uint2 tstack[JT_TRI_STACK];
   PersistLane L;
   bool live = false, more = true;
   int s = -1;
@@ -235,7 +234,7 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
     }
     unsigned pending = __ballot_sync(FULL, live || s >= 0);
     if (pending == 0u) break;
-    persist_traverse(S, L, stack, tstack, live, more);
+    persist_traverse(S, L, stack, live, more);
   }
   unsigned total = __reduce_add_sync(FULL, nrays);
   if (lane_id() == 0u && total) atomicAdd(counters + 1, (unsigned long long)total);

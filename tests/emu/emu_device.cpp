@@ -60,11 +60,11 @@ static void put_hit(jt_hit* o, const DHit& h) {
 
 // the persistent-warp traversal state machine (jt_dev_persist.cuh), one single-lane "warp" per ray
 static DHit persist_one(const JtDevScene& S, const DRay& r) {
-  uint2 stack[JT_WIDE_STACK], tstack[JT_TRI_STACK];
+  uint2 stack[JT_WIDE_STACK];
   PersistLane L;
   persist_init(L, S, r.o, r.d, r.tmin, r.tmax, S.wide_root, -1);
   bool live = S.wide_root >= 0;
-  persist_traverse(S, L, stack, tstack, live, false);
+  persist_traverse(S, L, stack, live, false);
   return DHit{L.best.t, L.best.u, L.best.v, L.best.inst, L.best.elem};
 }
 static unsigned long long g_wide_counts[3] = {0, 0, 0};
