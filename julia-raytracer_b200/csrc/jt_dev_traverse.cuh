@@ -255,26 +255,30 @@ JT_DEV uint32_t wide_node_hits(const float4* __restrict__ wnodes, uint32_t node,
   uint32_t qhiy[2] = {__float_as_uint(n4.x), __float_as_uint(n4.y)};
   uint32_t qhiz[2] = {__float_as_uint(n4.z), __float_as_uint(n4.w)};
   const bool px = R.d.x >= 0.0f, py = R.d.y >= 0.0f, pz = R.d.z >= 0.0f;
+  const uint32_t oct4 = R.oct * 0x01010101u;
   uint32_t hits = 0;
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     uint32_t nearx = px ? qlox[h] : qhix[h], farx = px ? qhix[h] : qlox[h];
     uint32_t neary = py ? qloy[h] : qhiy[h], fary = py ? qhiy[h] : qloy[h];
     uint32_t nearz = pz ? qloz[h] : qhiz[h], farz = pz ? qhiz[h] : qloz[h];
+    // decode the four meta bytes at once (branch-free, after Ylitie et al. 2017):
+    //   internal child: 0b001_11sss -> bit 24 + (slot ^ octant), 1 bit;  leaf: count<<5 | offset -> bits at offset;
+    //   empty slot: 0 -> contributes no bits
+    const uint32_t meta4 = meta_w[h];
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = (is_inner4 >> 4) * 7u;  // 0x07 in every internal byte
+    const uint32_t bit_index4 = (meta4 ^ (oct4 & inner_mask4)) & 0x1F1F1F1Fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      uint32_t meta = byte_of(meta_w[h], j);
       float t0x = fmaf(byte_as_biased_float(nearx, j), sx, alx), t1x = fmaf(byte_as_biased_float(farx, j), sx, ahx);
       float t0y = fmaf(byte_as_biased_float(neary, j), sy, aly), t1y = fmaf(byte_as_biased_float(fary, j), sy, ahy);
       float t0z = fmaf(byte_as_biased_float(nearz, j), sz, alz), t1z = fmaf(byte_as_biased_float(farz, j), sz, ahz);
       float lo = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
       float hi = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-      if (meta != 0u && lo <= hi) {
-        bool inner = (meta & 0x18u) == 0x18u;
-        uint32_t bit_index = inner ? (24u + ((meta & 7u) ^ R.oct)) : (meta & 31u);
-        uint32_t child_bits = inner ? 1u : (meta >> 5);
-        hits |= child_bits << bit_index;
-      }
+      uint32_t bits = byte_of(child_bits4, j) << byte_of(bit_index4, j);
+      hits |= (lo <= hi) ? bits : 0u;
     }
   }
   *ngroup_out = make_uint2(__float_as_uint(n1.x), (hits & 0xFF000000u) | imask);

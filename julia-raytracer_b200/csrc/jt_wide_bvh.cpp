@@ -21,6 +21,7 @@
 // The closest hit is order independent; exact-t ties are resolved with the per-octant visit
 // ranks computed here from the reference tree (SURVEY.md §8a "tie-break contract").
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -260,7 +261,7 @@ class Collapser {
     if (n == 1) return make_leaf();
     const int NB = 16;
     int best_axis = -1, best_bin = -1;
-    float best_cost = std::numeric_limits<float>::infinity();
+    float best_cost = std::numeric_limits<float>::infinity(), best_tri_cost = 0.0f;
     for (int ax = 0; ax < 3; ax++) {
       float lo = cbox.lo[ax], ext = cbox.hi[ax] - cbox.lo[ax];
       if (!(ext > 0.0f)) continue;
@@ -296,18 +297,24 @@ class Collapser {
         c += cnt[k];
         if (c == 0 || right_cnt[k + 1] == 0) continue;
         // wide-node aware cost: a slot holds up to 3 records, so count ceil(n/3) leaf slots per side
-        float cost = acc.area() * (float)((c + 2) / 3) + right_area[k + 1] * (float)((right_cnt[k + 1] + 2) / 3);
+        float cost = acc.area() * (float)((c + leaf_max_ - 1) / leaf_max_) +
+                     right_area[k + 1] * (float)((right_cnt[k + 1] + leaf_max_ - 1) / leaf_max_);
         if (cost < best_cost) {
           best_cost = cost;
           best_axis = ax;
           best_bin = k;
+          best_tri_cost = acc.area() * (float)c + right_area[k + 1] * (float)right_cnt[k + 1];
         }
       }
     }
-    if (n <= 3) {
-      // keep small groups together unless splitting clearly pays (leaf cost = 1 slot of the node box)
-      float leaf_cost = box.area();
-      if (best_axis < 0 || best_cost >= leaf_cost) return make_leaf();
+    if (n <= (size_t)leaf_max_) {
+      // Leaf or split? On the GPU one triangle test costs about as many issue slots as a whole 8-child node
+      // step (it runs at ~6 of 32 lanes, profiles/r01), so small groups are split whenever the children's
+      // boxes are tighter: cost = tri_cost * sum(area_k * n_k) + slab_cost * area(box) per extra slot.
+      float leaf_cost = tri_cost_ * box.area() * (float)n;
+      if (best_axis < 0) return make_leaf();
+      float split_cost = tri_cost_ * best_tri_cost + 2.0f * box.area();
+      if (split_cost >= leaf_cost) return make_leaf();
     }
     size_t m;
     if (best_axis < 0) {
@@ -560,6 +567,8 @@ class Collapser {
   const std::vector<JtHostInstance>& insts_;
   JtWideResult* out_;
   std::vector<ShapeRank> shape_ranks_;
+  int leaf_max_ = getenv("JT_LEAF_MAX") ? atoi(getenv("JT_LEAF_MAX")) : 3;          // experiment knobs
+  float tri_cost_ = getenv("JT_TRI_COST") ? (float)atof(getenv("JT_TRI_COST")) : 8.0f;
   std::vector<int> leaf_store_;  // record indices of leaves, contiguous per leaf
 };
 
