@@ -1,28 +1,27 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, smoke, bench (both arms), ncu launch list + one full capture.
-# Usage (from the repo root on the box): bash tools/gpu_round.sh [tag] [quick]
+# One GPU-box visit: smoke, parity tests, bench (both arms + the other configs), ncu launch list + full capture.
+# Usage (from the repo root on the box): bash tools/gpu_round.sh [tag]
 TAG=${1:-r01}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm,power.limit --format=csv > gpurun_out/gpu_${TAG}.csv 2>&1
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${TAG}.log 2>&1; echo "smoke exit $?" | tee -a gpurun_out/smoke_${TAG}.log
-timeout 1500 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu_${TAG}.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu_${TAG}.log
-tail -5 gpurun_out/pytest_gpu_${TAG}.log
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo "bench exit $?"
-cat gpurun_out/bench_${TAG}.json; tail -3 gpurun_out/bench_${TAG}.err
-timeout 900 python bench.py --steps 5 --warmup 3 --integrator megakernel --no-cpu-baseline > gpurun_out/bench_mega_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
-cut -c1-400 gpurun_out/bench_mega_${TAG}.json
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${TAG}.log 2>&1; echo "smoke exit $?" | tee -a gpurun_out/smoke_${TAG}.log
+timeout 900 python -m pytest tests -m gpu -x -q -s > gpurun_out/pytest_gpu_${TAG}.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu_${TAG}.log
+tail -3 gpurun_out/pytest_gpu_${TAG}.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err; echo "bench exit $?"
+cut -c1-400 gpurun_out/bench_${TAG}.json; tail -3 gpurun_out/bench_${TAG}.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2> gpurun_out/bench_ref_${TAG}.err; echo "bench ref exit $?"
 cut -c1-300 gpurun_out/bench_ref_${TAG}.json
 for sc in cornellbox features1 materials1 ecosys; do
-  timeout 600 python bench.py --scene $sc --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${sc}_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
-  cat gpurun_out/bench_${sc}_${TAG}.json | cut -c1-300
+  timeout 400 python bench.py --scene $sc --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${sc}_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
+  cut -c1-200 gpurun_out/bench_${sc}_${TAG}.json
 done
+timeout 300 python tools/bench_traverse.py classroom features1 ecosys > gpurun_out/traverse_${TAG}.json 2>>gpurun_out/bench_${TAG}.err
 # profiler passes: only after the identical plain command has exited 0
-PROF="python bench.py --steps 1 --warmup 1 --spp-per-step 2 --no-cpu-baseline"
-$PROF > gpurun_out/plain_${TAG}.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv $PROF > gpurun_out/ncu_launches_${TAG}.log 2>&1
+PROF="python bench.py --steps 1 --warmup 1 --spp-per-step 4 --no-cpu-baseline"
+timeout 300 $PROF > gpurun_out/plain_${TAG}.log 2>&1 && \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches_${TAG}.csv $PROF > gpurun_out/ncu_launches_${TAG}.log 2>&1
 echo "ncu launches exit $?"
-$PROF > gpurun_out/plain2_${TAG}.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k "regex:k_wf_(extend|shade|probe)" -s 6 -c 6 -o gpurun_out/prof_${TAG} -f $PROF > gpurun_out/ncu_full_${TAG}.log 2>&1
+timeout 300 $PROF > gpurun_out/plain2_${TAG}.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_wf_(extend|shade|probe)" -s 9 -c 3 -o gpurun_out/prof_${TAG} -f $PROF > gpurun_out/ncu_full_${TAG}.log 2>&1
 echo "ncu full exit $?"
-ls -la gpurun_out
+ls gpurun_out | head -40
