@@ -161,7 +161,8 @@ typedef struct {
   uint64_t scene_rays;        /* intersect_scene_bvh calls   (src/trace.jl:298,490) */
   uint64_t light_rays;        /* intersect_instance_bvh calls (src/trace.jl:1025) */
   uint64_t kernel_launches;   /* CUDA kernels launched by the library */
-  uint64_t _reserved[4];
+  uint64_t _reserved[4];      /* [0] microseconds spent in the extend (closest-hit) kernel, CUDA events
+                                 [1] number of extend launches                                         */
 } jt_counters;
 
 typedef struct jt_scene jt_scene; /* device-resident scene: SceneData + SceneBvh + TraceLights */

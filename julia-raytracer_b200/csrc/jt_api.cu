@@ -61,6 +61,10 @@ struct jt_scene {
   unsigned long long* d_counters = nullptr;  // [0] camera paths [1] scene rays [2] light rays
   uint64_t launches = 0;
   unsigned persist_blocks = 0;
+  // device time of the dominant kernel (extend), measured with CUDA events around every launch
+  cudaEvent_t ext_ev[16] = {};
+  double extend_ms = 0.0;
+  uint64_t extend_launches = 0;
   std::vector<jt_state*> states;  // for flushing lazily batched sample ranges
   jt_scene_stats stats;
   int64_t device_bytes = 0;
@@ -115,6 +119,8 @@ extern "C" void jt_scene_destroy(jt_scene* sc) {
   for (jt_state* st : sc->states) st->has_pending = false;
   cudaSetDevice(sc->device);
   for (void* p : sc->allocs) cudaFree(p);
+  for (int k = 0; k < 16; k++)
+    if (sc->ext_ev[k]) cudaEventDestroy(sc->ext_ev[k]);
   if (sc->ev_start) cudaEventDestroy(sc->ev_start);
   if (sc->ev_stop) cudaEventDestroy(sc->ev_stop);
   if (sc->stream) cudaStreamDestroy(sc->stream);
@@ -130,6 +136,7 @@ static int scene_create_impl(const jt_scene_desc* d, int device, jt_scene* sc) {
   JT_CUDA(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
   JT_CUDA(cudaEventCreate(&sc->ev_start));
   JT_CUDA(cudaEventCreate(&sc->ev_stop));
+  for (int k = 0; k < 16; k++) JT_CUDA(cudaEventCreate(&sc->ext_ev[k]));
   memset(&sc->dev, 0, sizeof(sc->dev));
   memset(&sc->stats, 0, sizeof(sc->stats));
 
@@ -221,9 +228,13 @@ extern "C" int jt_scene_counters(jt_scene* sc, jt_counters* out, int reset) {
   out->scene_rays = h[1];
   out->light_rays = h[2];
   out->kernel_launches = sc->launches;
+  out->_reserved[0] = (uint64_t)(sc->extend_ms * 1000.0);  // microseconds in the extend (closest-hit) kernel
+  out->_reserved[1] = sc->extend_launches;
   if (reset) {
     JT_CUDA(cudaMemset(sc->d_counters, 0, sizeof(h)));
     sc->launches = 0;
+    sc->extend_ms = 0.0;
+    sc->extend_launches = 0;
   }
   return JT_OK;
 }
@@ -592,12 +603,15 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
     // shrink, because every slot appears at most once per iteration)
     unsigned ge = (unsigned)((remaining + 127) / 128), gs = (unsigned)((remaining + 32 * WF_NKEY + 127) / 128);
     (void)g_ext; (void)g_shade;
+    const int evi = 2 * (it % poll_every);
+    JT_CUDA(cudaEventRecord(sc->ext_ev[evi], q));
     if (MODE == MODE_WIDE) {
       unsigned gp = std::min<unsigned>((unsigned)((remaining + JT_PERSIST_BLOCK - 1) / JT_PERSIST_BLOCK), persist_grid(sc));
       k_wf_extend_persist<<<gp, JT_PERSIST_BLOCK, 0, q>>>(sc->dev, B, cur, sc->d_counters);
     } else {
       k_wf_extend<MODE><<<ge, 128, 0, q>>>(sc->dev, B, cur, sc->d_counters);
     }
+    JT_CUDA(cudaEventRecord(sc->ext_ev[evi + 1], q));
     if (P.sampler == 1) {
       k_wf_shade<1><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
       k_wf_probe<MODE><<<ge, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
@@ -612,6 +626,11 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
     if ((it + 1) % poll_every == 0) {
       JT_CUDA(cudaMemcpyAsync(st->h_counts, B.counts, WF_C_TOTAL * 4, cudaMemcpyDeviceToHost, q));
       JT_CUDA(cudaStreamSynchronize(q));
+      for (int k = 0; k < poll_every; k++) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, sc->ext_ev[2 * k], sc->ext_ev[2 * k + 1]) == cudaSuccess) sc->extend_ms += ms;
+        sc->extend_launches++;
+      }
       remaining = st->h_counts[WF_C_EXT0 + cur];
       if (remaining == 0) break;
     }

@@ -67,7 +67,8 @@ class DeviceScene:
         c = A.jt_counters()
         _lib.check(self.L.jt_scene_counters(self.h, C.byref(c), int(reset)))
         return dict(camera_paths=int(c.camera_paths), scene_rays=int(c.scene_rays),
-                    light_rays=int(c.light_rays), kernel_launches=int(c.kernel_launches))
+                    light_rays=int(c.light_rays), kernel_launches=int(c.kernel_launches),
+                    extend_us=int(c._reserved[0]), extend_launches=int(c._reserved[1]))
 
     def synchronize(self):
         _lib.check(self.L.jt_synchronize(self.h))

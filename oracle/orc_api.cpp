@@ -154,11 +154,12 @@ ORC_API void orc_light_cdf(void* h, int64_t i, float* out) {
 }
 
 // ---- "identical rays" hooks ----------------------------------------------------------------------
-// counters_out (optional): 8 x uint64 {scene_rays, light_rays, camera_paths, tlas_nodes, blas_nodes,
-// instance_visits, tri_tests, quad_tests}
+// counters_out (optional): 11 x uint64 {scene_rays, light_rays, camera_paths, tlas_nodes, blas_nodes,
+// instance_visits, tri_tests, quad_tests, probe_blas_nodes, probe_tri_tests, probe_quad_tests}
 static void export_counters(const Counters& c, uint64_t* out) {
   out[0] = c.scene_rays; out[1] = c.light_rays; out[2] = c.camera_paths; out[3] = c.tlas_nodes;
   out[4] = c.blas_nodes; out[5] = c.instance_visits; out[6] = c.tri_tests; out[7] = c.quad_tests;
+  out[8] = c.probe_blas_nodes; out[9] = c.probe_tri_tests; out[10] = c.probe_quad_tests;
 }
 
 ORC_API void orc_intersect(void* h, const jt_ray* rays, int64_t n, jt_hit* out, uint64_t* counters_out, int threads) {

@@ -84,10 +84,13 @@ inline SceneIsec no_scene_isec() { return SceneIsec{-1, -1, V2{0, 0}, 0.0f, fals
 struct Counters {
   uint64_t scene_rays = 0, light_rays = 0, camera_paths = 0;
   uint64_t tlas_nodes = 0, blas_nodes = 0, instance_visits = 0, tri_tests = 0, quad_tests = 0;
+  // the share of the above spent inside intersect_instance_bvh (light-pdf probes)
+  uint64_t probe_blas_nodes = 0, probe_tri_tests = 0, probe_quad_tests = 0;
   void add(const Counters& o) {
     scene_rays += o.scene_rays; light_rays += o.light_rays; camera_paths += o.camera_paths;
     tlas_nodes += o.tlas_nodes; blas_nodes += o.blas_nodes; instance_visits += o.instance_visits;
     tri_tests += o.tri_tests; quad_tests += o.quad_tests;
+    probe_blas_nodes += o.probe_blas_nodes; probe_tri_tests += o.probe_tri_tests; probe_quad_tests += o.probe_quad_tests;
   }
 };
 
@@ -356,7 +359,13 @@ inline SceneIsec intersect_instance_bvh(const Scene& scene, int64_t instance_, R
   const Instance& inst = scene.instances[instance_ - 1];
   if (cnt) { cnt->light_rays++; cnt->instance_visits++; }
   Ray inv_ray = transform_ray(inverse(inst.frame, true), ray);
+  uint64_t n0 = cnt ? cnt->blas_nodes : 0, t0 = cnt ? cnt->tri_tests : 0, q0 = cnt ? cnt->quad_tests : 0;
   ShapeIsec s = intersect_shape_bvh(scene.shapes[inst.shape - 1], inv_ray, find_any, cnt);
+  if (cnt) {
+    cnt->probe_blas_nodes += cnt->blas_nodes - n0;
+    cnt->probe_tri_tests += cnt->tri_tests - t0;
+    cnt->probe_quad_tests += cnt->quad_tests - q0;
+  }
   if (!s.hit) return no_scene_isec();
   return SceneIsec{instance_, s.element, s.uv, s.distance, true};
 }

@@ -64,7 +64,8 @@ def lib():
 
 
 COUNTER_NAMES = ["scene_rays", "light_rays", "camera_paths", "tlas_nodes", "blas_nodes",
-                 "instance_visits", "tri_tests", "quad_tests"]
+                 "instance_visits", "tri_tests", "quad_tests", "probe_blas_nodes", "probe_tri_tests",
+                 "probe_quad_tests"]
 
 
 def make_params(**kw) -> "A.jt_params":
@@ -115,7 +116,7 @@ class Oracle:
     def intersect(self, rays: np.ndarray, threads=0, counters=False):
         rays = np.ascontiguousarray(rays, dtype=A.RAY_DTYPE)
         hits = np.zeros(len(rays), A.HIT_DTYPE)
-        cnt = np.zeros(8, np.uint64)
+        cnt = np.zeros(11, np.uint64)
         self.L.orc_intersect(self.h, rays.ctypes.data, len(rays), hits.ctypes.data, cnt.ctypes.data, threads)
         return (hits, dict(zip(COUNTER_NAMES, (int(x) for x in cnt)))) if counters else hits
 
@@ -164,7 +165,7 @@ class Oracle:
         return dict(image=image, albedo=albedo, normal=normal, hits=hits, samples=s.value)
 
     def counters(self, reset=False):
-        cnt = np.zeros(8, np.uint64)
+        cnt = np.zeros(11, np.uint64)
         self.L.orc_get_counters(self.h, cnt.ctypes.data, int(reset))
         return dict(zip(COUNTER_NAMES, (int(x) for x in cnt)))
 
@@ -174,6 +175,17 @@ def algorithmic_bytes(c: dict) -> int:
     rays = c["scene_rays"] + c["light_rays"]
     return (56 * rays + 32 * (c["tlas_nodes"] + c["blas_nodes"]) + 48 * c["instance_visits"]
             + 36 * c["tri_tests"] + 48 * c["quad_tests"])
+
+
+def algorithmic_bytes_probe(c: dict) -> int:
+    """The part of algorithmic_bytes() spent in intersect_instance_bvh (light-pdf probes)."""
+    return (56 * c["light_rays"] + 32 * c["probe_blas_nodes"] + 48 * c["light_rays"]
+            + 36 * c["probe_tri_tests"] + 48 * c["probe_quad_tests"])
+
+
+def algorithmic_bytes_scene(c: dict) -> int:
+    """The part spent in intersect_scene_bvh (what the extend kernel replaces)."""
+    return algorithmic_bytes(c) - algorithmic_bytes_probe(c)
 
 
 def fmath(fn: int, x, y=None):

@@ -27,6 +27,8 @@ for scene, sampler, res, spp in [("cornellbox", "naive", 360, 8), ("cornellbox",
     b = orc.algorithmic_bytes(c)
     out[f"{scene}_{sampler}"] = {
         "bytes_per_sample": b / c["camera_paths"] + 16.0, "bytes_per_ray": b / rays,
+        "scene_bytes_per_scene_ray": orc.algorithmic_bytes_scene(c) / c["scene_rays"],
+        "probe_bytes_per_light_ray": (orc.algorithmic_bytes_probe(c) / c["light_rays"]) if c["light_rays"] else 0.0,
         "rays_per_sample": rays / c["camera_paths"], "scene_rays_per_sample": c["scene_rays"] / c["camera_paths"],
         "light_rays_per_sample": c["light_rays"] / c["camera_paths"],
         "nodes_per_ray": (c["tlas_nodes"] + c["blas_nodes"]) / rays, "instance_visits_per_ray": c["instance_visits"] / rays,
