@@ -35,5 +35,39 @@ for scene, sampler, res, spp in [("cornellbox", "naive", 360, 8), ("cornellbox",
         "tri_tests_per_ray": c["tri_tests"] / rays, "quad_tests_per_ray": c["quad_tests"] / rays,
         "measured_on": f"{w}x{h} x {spp} spp, oracle, reference traversal order", "source": "profiles/algorithmic_bytes.json"}
     print(scene, sampler, json.dumps(out[f"{scene}_{sampler}"]), flush=True)
+# bytes the wide-BVH kernel itself walks per scene ray (80 B nodes, 48 B triangle records, 112 B instance
+# records, 56 B ray in / hit out), counted by the host-stepped device code on camera rays + 3 diffuse bounces
+import importlib  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+import emu  # noqa: E402
+import raygen  # noqa: E402
+
+bvhm = importlib.import_module("julia-raytracer_b200.bvh")
+lm = importlib.import_module("julia-raytracer_b200.lights")
+for key in list(out):
+    scene = key.rsplit("_", 1)[0]
+    sc = orc.jt.load_scene(os.path.join(ROOT, "assets", "scenes", f"{scene}.jtscene"))
+    b = bvhm.make_scene_bvh(sc)
+    lt = lm.make_trace_lights(sc)
+    o, e = orc.Oracle(sc, b, lt), emu.Emu(sc, b, lt)
+    p = orc.make_params(resolution=320)
+    w, h = o.make_state(p)
+    cur = raygen.camera_rays(o, p, w, h, 60000, seed=9)
+    rays = [cur]
+    for g in range(3):
+        cur = raygen.secondary_rays(cur, o.intersect(cur), seed=10 + g)
+        if len(cur) == 0:
+            break
+        rays.append(cur)
+    rays = np.concatenate(rays)
+    emu.wide_counts()
+    e.intersect(rays, 0)
+    wc = emu.wide_counts()
+    out[key]["wide_bytes_per_scene_ray"] = 56 + (80 * wc["nodes"] + 48 * wc["prims"] + 112 * wc["instances"]) / len(rays)
+    out[key]["wide_nodes_per_scene_ray"] = wc["nodes"] / len(rays)
+    out[key]["wide_prims_per_scene_ray"] = wc["prims"] / len(rays)
+    print(key, "as implemented:", round(out[key]["wide_bytes_per_scene_ray"]), "B per scene ray", flush=True)
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "profiles", "algorithmic_bytes.json"), "w"), indent=1)
