@@ -196,6 +196,9 @@ JT_API int jt_state_reset(jt_state* state);
  * In accumulate = 1 mode the sums are divided by `state.samples` first. */
 JT_API int jt_state_download(jt_state* state, float* image_rgba, float* albedo_rgb,
                              float* normal_rgb, int64_t* hits);
+/* N3: the reference's save path on the GPU -- rgb_to_srgb (src/color.jl:25-29), clamp01nan and 8-bit
+ * quantisation of save_image (src/sceneio.jl:97-113): width*height RGBA8, row-major, ready for the PNG writer. */
+JT_API int jt_state_download_srgb8(jt_state* state, uint8_t* rgba8);
 /* Raw device pointers of the accumulators (float4 image, float4-padded albedo / normal, int32
  * hits) so that a host that owns a communicator (torch.distributed / NCCL) can reduce them in
  * place across GPUs. `count` = width*height. */

@@ -19,7 +19,7 @@ EXPORTS = [
     "jt_state_size", "jt_state_reset", "jt_state_download", "jt_state_device_buffers",
     "jt_state_set_samples", "jt_trace_samples", "jt_trace_sample_range", "jt_synchronize",
     "jt_elapsed_ms", "jt_intersect", "jt_intersect_instance", "jt_sample_camera",
-    "jt_intersect_device", "jt_make_bvh",
+    "jt_intersect_device", "jt_make_bvh", "jt_state_download_srgb8",
 ]
 
 
@@ -56,6 +56,7 @@ def lib() -> C.CDLL:
     L.jt_state_size.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.jt_state_reset.argtypes = [vp]
     L.jt_state_download.argtypes = [vp, vp, vp, vp, vp]
+    L.jt_state_download_srgb8.argtypes = [vp, vp]
     L.jt_state_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                                           C.POINTER(i64)]
     L.jt_state_set_samples.argtypes = [vp, i32]

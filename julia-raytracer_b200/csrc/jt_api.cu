@@ -381,6 +381,26 @@ __global__ void k_finalize(const float4* __restrict__ image, const float4* __res
   if (out_hits) out_hits[i] = hits[i];
 }
 
+// N3: the save path on the GPU. rgb_to_srgb (src/color.jl:25-29) + clamp01nan + 8-bit quantisation
+// of save_image (src/sceneio.jl:97-113). Julia's `^(rgb, 1/2.4f0)` is Float32(exp2(log2(Float64(x)) * Float64(y))).
+__global__ void k_srgb8(const float4* __restrict__ image, long long n, float scale, uchar4* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = image[i];
+  float c[4] = {p.x * scale, p.y * scale, p.z * scale, p.w * scale};
+  unsigned char b[4];
+  const double expo = (double)(1.0f / 2.4f);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float v = c[k];
+    if (k < 3) v = (v <= 0.0031308f) ? 12.92f * v : 1.055f * (float)exp2(log2((double)v) * expo) - 0.055f;
+    if (!(v == v)) v = 0.0f;              // clamp01nan: NaN -> 0
+    v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+    b[k] = (unsigned char)__float2int_rn(v * 255.0f);
+  }
+  out[i] = make_uchar4(b[0], b[1], b[2], b[3]);
+}
+
 // =================================================================================================
 // state
 // =================================================================================================
@@ -526,6 +546,25 @@ extern "C" int jt_state_download(jt_state* st, float* image, float* albedo, floa
   if (albedo) memcpy(albedo, hp + n * 16, (size_t)n * 12);
   if (normal) memcpy(normal, hp + n * 28, (size_t)n * 12);
   if (hits) memcpy(hits, hp + n * 40, (size_t)n * 8);
+  return JT_OK;
+}
+
+extern "C" int jt_state_download_srgb8(jt_state* st, uint8_t* rgba8) {
+  if (!st || !rgba8) return jt_set_error(JT_ERR_INVALID, "jt_state_download_srgb8: null argument");
+  jt_scene* sc = st->scene;
+  JT_CUDA(cudaSetDevice(sc->device));
+  int frc = flush_state(st);
+  if (frc) return frc;
+  long long n = (long long)st->width * st->height;
+  if (!st->d_pack) JT_CUDA(cudaMalloc(&st->d_pack, (size_t)n * 48));
+  if (!st->h_pack) JT_CUDA(cudaHostAlloc(&st->h_pack, (size_t)n * 48, cudaHostAllocDefault));
+  float scale = (st->accumulate == 1 && st->samples > 0) ? 1.0f / (float)st->samples : 1.0f;
+  k_srgb8<<<(unsigned)((n + 255) / 256), 256, 0, sc->stream>>>(st->dev.image, n, scale, (uchar4*)st->d_pack);
+  sc->launches++;
+  JT_CUDA(cudaGetLastError());
+  JT_CUDA(cudaMemcpyAsync(st->h_pack, st->d_pack, (size_t)n * 4, cudaMemcpyDeviceToHost, sc->stream));
+  JT_CUDA(cudaStreamSynchronize(sc->stream));
+  memcpy(rgba8, st->h_pack, (size_t)n * 4);
   return JT_OK;
 }
 

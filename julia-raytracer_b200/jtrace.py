@@ -12,7 +12,7 @@ from .bvh import make_scene_bvh
 from .cli import Params, parse_cli_args
 from .lights import make_trace_lights
 from .scene import find_camera
-from .sceneio import load_scene, save_image
+from .sceneio import load_scene, save_image, save_srgb8  # noqa: F401
 from .trace import DeviceScene, get_image, make_trace_state, trace_samples
 
 
@@ -85,7 +85,7 @@ def main(params: Union[str, Params, None], device: int = 0) -> Optional[dict]:
         c["camera_paths"] / render_s / 1e6, rays / render_s / 1e6, c["scene_rays"], c["light_rays"]))
     print("saving image...")
     image = get_image(state)
-    save_image(params.output, image)
+    save_srgb8(params.output, state.srgb8())  # rgb_to_srgb + 8-bit quantisation done on the GPU (N3)
     print("saved image to", params.output)
     print(f"total time: {format_seconds(time.time() - render_start)}")
     return dict(image=image, state=state, counters=c, render_seconds=render_s)

@@ -449,3 +449,15 @@ def save_image(filename: str, image_rgba: np.ndarray) -> None:
     if d:
         os.makedirs(d, exist_ok=True)
     Image.fromarray(image_to_srgb8(image_rgba), "RGBA").save(filename)
+
+
+def save_srgb8(filename: str, rgba8: np.ndarray) -> None:
+    """Write an already display-encoded (H, W, 4) uint8 image (what jt_state_download_srgb8 returns)."""
+    ext = os.path.splitext(filename)[1].lower()
+    if ext != ".png":
+        raise ValueError(f"{ext} is not supported")
+    from PIL import Image
+    d = os.path.dirname(filename)
+    if d:
+        os.makedirs(d, exist_ok=True)
+    Image.fromarray(np.ascontiguousarray(rgba8, np.uint8), "RGBA").save(filename)

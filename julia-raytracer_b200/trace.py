@@ -134,6 +134,12 @@ class TraceState:
                                             self.normal.ctypes.data, self.hits.ctypes.data))
         return self
 
+    def srgb8(self) -> np.ndarray:
+        """(H, W, 4) uint8 sRGB image converted on the GPU (the reference's save path)."""
+        out = np.zeros((self.height, self.width, 4), np.uint8)
+        _lib.check(self.L.jt_state_download_srgb8(self.h, out.ctypes.data))
+        return out
+
     def reset(self):
         _lib.check(self.L.jt_state_reset(self.h))
 

@@ -173,6 +173,20 @@ def test_sum_mode_and_logical_shards(pair):
     assert np.array_equal(whole.hits, mean.hits)
 
 
+def test_srgb8_output_matches_host_save_path(pair):
+    """N3: GPU rgb_to_srgb + clamp + 8-bit quantise vs the host formula (+-1 LSB: third-party rounding)."""
+    o, d = pair("features1")
+    p = _params(samples=4, batch=4, sampler=1, resolution=96)
+    st = trace.make_trace_state(d, p)
+    trace.trace_samples(st, d, None, None, p)
+    st.sync()
+    gpu = st.srgb8().astype(np.int32)
+    host = jt.sceneio.image_to_srgb8(st.image.reshape(st.height, st.width, 4)).astype(np.int32)
+    assert gpu.shape == host.shape
+    assert np.abs(gpu - host).max() <= 1 and (gpu != host).mean() < 0.01
+    st.close()
+
+
 def test_error_paths(pair, scenes):
     o, d = pair("cornellbox")
     L = d.L

@@ -1,0 +1,27 @@
+"""Driver of tools/asan_emu.sh (ASan/UBSan over the host-stepped device code)."""
+import os, sys, ctypes as C
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests')); sys.path.insert(0, ROOT)
+import orc, emu, raygen, synth, numpy as np, importlib
+# swap in the ASan build
+L = C.CDLL(os.environ.get('JT_EMU_LIB', '/tmp/libjt_emu_asan.so'))
+for name in ['emu_create','emu_destroy','emu_last_error','emu_stats','emu_intersect','emu_intersect_instance','emu_trace_range','emu_trace_wavefront','emu_wide_counts']:
+    pass
+emu._LIB = None
+real = emu.lib()
+for name in ['emu_create','emu_destroy','emu_last_error','emu_stats','emu_intersect','emu_intersect_instance','emu_trace_range','emu_trace_wavefront','emu_wide_counts']:
+    f = getattr(L, name); g = getattr(real, name); f.restype = g.restype; f.argtypes = g.argtypes
+emu._LIB = L
+bvhm=importlib.import_module('julia-raytracer_b200.bvh'); lm=importlib.import_module('julia-raytracer_b200.lights')
+for s in ['synthetic_all','synthetic_one','cornellbox','features1','classroom','ecosys']:
+    sc = synth.make_scene(s) if s.startswith('synth') else orc.jt.load_scene(os.path.join(ROOT, 'assets', 'scenes', f'{s}.jtscene'))
+    b=bvhm.make_scene_bvh(sc); Lt=lm.make_trace_lights(sc)
+    o=orc.Oracle(sc,b,Lt); e=emu.Emu(sc,b,Lt)
+    p=orc.make_params(resolution=48, samples=2, batch=2, sampler=1); w,h=o.make_state(p)
+    rays=raygen.camera_rays(o,p,w,h,3000,seed=3); sec=raygen.secondary_rays(rays,o.intersect(rays),seed=4)
+    for trav in (0,1,3): e.intersect(np.concatenate([rays,sec]),trav)
+    for sampler in (1,2):
+        for trav in (0,1):
+            p=orc.make_params(resolution=32, samples=2, batch=2, sampler=sampler, traversal=trav)
+            e.trace(p,32,max(1,int(32/ float(sc.cameras[0].aspect))),0,2,wavefront=True); e.trace(p,32,max(1,int(32/float(sc.cameras[0].aspect))),0,2,wavefront=False)
+    print('asan ok', s, flush=True)
