@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -70,6 +71,7 @@ struct jt_scene {
   int64_t device_bytes = 0;
 };
 
+#define JT_MAX_PIPES 4
 struct jt_state {
   jt_scene* scene = nullptr;
   int width = 0, height = 0, samples = 0;
@@ -77,9 +79,12 @@ struct jt_state {
   DevState dev;
   // wavefront integrator (allocated on first use)
   bool wf_ready = false;
-  WfBuffers wf;
+  int npipe = 1;              // the image is split over npipe independent wavefront pipelines (own stream each)
+  WfBuffers wf[JT_MAX_PIPES];
+  cudaStream_t pipe_stream[JT_MAX_PIPES] = {};
+  cudaEvent_t pipe_done[JT_MAX_PIPES] = {};
   std::vector<void*> wf_allocs;
-  int* h_counts = nullptr;  // pinned mirror of wf.counts
+  int* h_counts = nullptr;  // pinned mirror of the pipelines' counters (WF_C_TOTAL ints each)
   // download staging (allocated on first download)
   void* d_pack = nullptr;
   void* h_pack = nullptr;
@@ -92,6 +97,9 @@ struct jt_state {
 };
 
 #define JT_LAZY_SPP 32
+#ifndef JT_DEFAULT_PIPES
+#define JT_DEFAULT_PIPES 2 /* measured on B200: 338 -> 357 Msamples/s (classroom), profiles/r01/tuning_variants.txt */
+#endif
 static int flush_state(jt_state* st);
 static int flush_scene(jt_scene* sc) {
   for (jt_state* st : sc->states) {
@@ -481,6 +489,10 @@ extern "C" void jt_state_destroy(jt_state* st) {
   cudaStreamSynchronize(st->scene->stream);
   cudaFree(st->dev.image); cudaFree(st->dev.albedo); cudaFree(st->dev.normal); cudaFree(st->dev.hits);
   for (void* p : st->wf_allocs) cudaFree(p);
+  for (int k = 1; k < JT_MAX_PIPES; k++)
+    if (st->pipe_stream[k]) cudaStreamDestroy(st->pipe_stream[k]);
+  for (int k = 0; k < JT_MAX_PIPES; k++)
+    if (st->pipe_done[k]) cudaEventDestroy(st->pipe_done[k]);
   if (st->h_counts) cudaFreeHost(st->h_counts);
   if (st->d_pack) cudaFree(st->d_pack);
   if (st->h_pack) cudaFreeHost(st->h_pack);
@@ -598,81 +610,128 @@ static unsigned persist_grid(jt_scene* sc);
 
 static int wf_prepare(jt_scene* sc, jt_state* st) {
   if (st->wf_ready) return JT_OK;
-  size_t n = (size_t)st->width * st->height;
-  WfBuffers& B = st->wf;
-  memset(&B, 0, sizeof(B));
-  B.n = (int)n;
+  const size_t total = (size_t)st->width * st->height;
+  int npipe = getenv("JT_PIPELINES") ? atoi(getenv("JT_PIPELINES")) : JT_DEFAULT_PIPES;
+  npipe = std::max(1, std::min(JT_MAX_PIPES, npipe));
+  if (total < 65536) npipe = 1;
+  st->npipe = npipe;
   auto alloc = [&](void** out, size_t bytes) -> int {
     JT_CUDA(cudaMalloc(out, bytes));
     st->wf_allocs.push_back(*out);
     return JT_OK;
   };
-  int rc;
-  if ((rc = alloc((void**)&B.ray0, n * 16)) || (rc = alloc((void**)&B.ray1, n * 16)) || (rc = alloc((void**)&B.hit0, n * 16)) ||
-      (rc = alloc((void**)&B.wgt, n * 16)) || (rc = alloc((void**)&B.rad, n * 16)) || (rc = alloc((void**)&B.bsdf, n * 16)) ||
-      (rc = alloc((void**)&B.alb, n * 16)) || (rc = alloc((void**)&B.nrm, n * 16)) || (rc = alloc((void**)&B.med0, n * 16)) ||
-      (rc = alloc((void**)&B.med1, n * 16)) || (rc = alloc((void**)&B.ctl, n * 16)) ||
-      (rc = alloc((void**)&B.q_ext[0], n * 4)) || (rc = alloc((void**)&B.q_ext[1], n * 4)) ||
-      (rc = alloc((void**)&B.q_shade, n * 4 * WF_NKEY)) || (rc = alloc((void**)&B.q_probe, n * 4)) ||
-      (rc = alloc((void**)&B.counts, WF_C_TOTAL * 4)))
-    return rc;
-  JT_CUDA(cudaHostAlloc((void**)&st->h_counts, WF_C_TOTAL * 4, cudaHostAllocDefault));
+  size_t base = 0;
+  for (int k = 0; k < npipe; k++) {
+    // contiguous pixel ranges, warp-aligned
+    size_t n = (k == npipe - 1) ? total - base : ((total / (size_t)npipe + 31) & ~(size_t)31);
+    WfBuffers& B = st->wf[k];
+    memset(&B, 0, sizeof(B));
+    B.n = (int)n;
+    B.pixel_base = (int)base;
+    base += n;
+    int rc;
+    if ((rc = alloc((void**)&B.ray0, n * 16)) || (rc = alloc((void**)&B.ray1, n * 16)) || (rc = alloc((void**)&B.hit0, n * 16)) ||
+        (rc = alloc((void**)&B.wgt, n * 16)) || (rc = alloc((void**)&B.rad, n * 16)) || (rc = alloc((void**)&B.bsdf, n * 16)) ||
+        (rc = alloc((void**)&B.alb, n * 16)) || (rc = alloc((void**)&B.nrm, n * 16)) || (rc = alloc((void**)&B.med0, n * 16)) ||
+        (rc = alloc((void**)&B.med1, n * 16)) || (rc = alloc((void**)&B.ctl, n * 16)) ||
+        (rc = alloc((void**)&B.q_ext[0], n * 4)) || (rc = alloc((void**)&B.q_ext[1], n * 4)) ||
+        (rc = alloc((void**)&B.q_shade, n * 4 * WF_NKEY)) || (rc = alloc((void**)&B.q_probe, n * 4)) ||
+        (rc = alloc((void**)&B.counts, WF_C_TOTAL * 4)))
+      return rc;
+    st->pipe_stream[k] = sc->stream;
+    if (k > 0) JT_CUDA(cudaStreamCreateWithFlags(&st->pipe_stream[k], cudaStreamNonBlocking));
+    JT_CUDA(cudaEventCreateWithFlags(&st->pipe_done[k], cudaEventDisableTiming));
+  }
+  JT_CUDA(cudaHostAlloc((void**)&st->h_counts, JT_MAX_PIPES * WF_C_TOTAL * 4, cudaHostAllocDefault));
   st->wf_ready = true;
   return JT_OK;
 }
 
 // Host-driven wavefront loop: generate, then (extend, shade, probe, advance) until the extend queue is
 // empty. Queue sizes stay on the device; the host only polls the next-queue length every few iterations.
+// The image is split over npipe pipelines that run on their own streams with a share of the persistent grid,
+// so one pipeline's latency-bound shade / probe kernels and kernel tails overlap the other's issue-bound extend.
 template <int MODE>
 static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int begin, int end) {
   int rc = wf_prepare(sc, st);
   if (rc) return rc;
-  WfBuffers& B = st->wf;
-  const int n = B.n;
-  cudaStream_t q = sc->stream;
-  k_wf_generate<<<(n + 255) / 256, 256, 0, q>>>(sc->dev, B, P, begin, end, sc->d_counters);
-  sc->launches++;
-  const unsigned g_ext = (unsigned)((n + 127) / 128), g_shade = (unsigned)((n + 32 * WF_NKEY + 127) / 128);
-  int cur = 0;
-  int remaining = n;
+  const int npipe = st->npipe;
   const int poll_every = 4;
+  int cur[JT_MAX_PIPES], remaining[JT_MAX_PIPES];
+  bool active[JT_MAX_PIPES];
+  // the other pipelines start after everything already enqueued on the main stream
+  for (int k = 1; k < npipe; k++) {
+    JT_CUDA(cudaEventRecord(st->pipe_done[0], sc->stream));
+    JT_CUDA(cudaStreamWaitEvent(st->pipe_stream[k], st->pipe_done[0], 0));
+  }
+  for (int k = 0; k < npipe; k++) {
+    WfBuffers& B = st->wf[k];
+    k_wf_generate<<<(B.n + 255) / 256, 256, 0, st->pipe_stream[k]>>>(sc->dev, B, P, begin, end, sc->d_counters);
+    sc->launches++;
+    cur[k] = 0;
+    remaining[k] = B.n;
+    active[k] = true;
+  }
+  const int pdiv = getenv("JT_PGRID_DIV") ? atoi(getenv("JT_PGRID_DIV")) : 1;
+  const unsigned pgrid = std::max(1u, persist_grid(sc) / (unsigned)std::max(1, pdiv));
   for (int it = 0;; it++) {
-    int next = cur ^ 1;
-    // grids sized from the last polled queue length (an upper bound until the next poll: queues only
-    // shrink, because every slot appears at most once per iteration)
-    unsigned ge = (unsigned)((remaining + 127) / 128), gs = (unsigned)((remaining + 32 * WF_NKEY + 127) / 128);
-    (void)g_ext; (void)g_shade;
-    const int evi = 2 * (it % poll_every);
-    JT_CUDA(cudaEventRecord(sc->ext_ev[evi], q));
-    if (MODE == MODE_WIDE) {
-      unsigned gp = std::min<unsigned>((unsigned)((remaining + JT_PERSIST_BLOCK - 1) / JT_PERSIST_BLOCK), persist_grid(sc));
-      k_wf_extend_persist<<<gp, JT_PERSIST_BLOCK, 0, q>>>(sc->dev, B, cur, sc->d_counters);
-    } else {
-      k_wf_extend<MODE><<<ge, 128, 0, q>>>(sc->dev, B, cur, sc->d_counters);
-    }
-    JT_CUDA(cudaEventRecord(sc->ext_ev[evi + 1], q));
-    if (P.sampler == 1) {
-      k_wf_shade<1><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
-      k_wf_probe<MODE><<<ge, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
-      sc->launches += 4;
-    } else {
-      k_wf_shade<2><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
-      sc->launches += 3;
-    }
-    k_wf_advance<<<1, 32, 0, q>>>(B, cur);
-    st->wf_iterations++;
-    cur = next;
-    if ((it + 1) % poll_every == 0) {
-      JT_CUDA(cudaMemcpyAsync(st->h_counts, B.counts, WF_C_TOTAL * 4, cudaMemcpyDeviceToHost, q));
-      JT_CUDA(cudaStreamSynchronize(q));
-      for (int k = 0; k < poll_every; k++) {
-        float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, sc->ext_ev[2 * k], sc->ext_ev[2 * k + 1]) == cudaSuccess) sc->extend_ms += ms;
-        sc->extend_launches++;
+    for (int k = 0; k < npipe; k++) {
+      if (!active[k]) continue;
+      WfBuffers& B = st->wf[k];
+      cudaStream_t q = st->pipe_stream[k];
+      const int next = cur[k] ^ 1;
+      // grids sized from the last polled queue length (an upper bound until the next poll: queues only
+      // shrink, because every slot appears at most once per iteration)
+      unsigned ge = (unsigned)((remaining[k] + 127) / 128), gs = (unsigned)((remaining[k] + 32 * WF_NKEY + 127) / 128);
+      const int evi = 2 * (it % poll_every);
+      if (k == 0) JT_CUDA(cudaEventRecord(sc->ext_ev[evi], q));
+      if (MODE == MODE_WIDE) {
+        unsigned gp = std::min<unsigned>((unsigned)((remaining[k] + JT_PERSIST_BLOCK - 1) / JT_PERSIST_BLOCK), pgrid);
+        k_wf_extend_persist<<<gp, JT_PERSIST_BLOCK, 0, q>>>(sc->dev, B, cur[k], sc->d_counters);
+      } else {
+        k_wf_extend<MODE><<<ge, 128, 0, q>>>(sc->dev, B, cur[k], sc->d_counters);
       }
-      remaining = st->h_counts[WF_C_EXT0 + cur];
-      if (remaining == 0) break;
+      if (k == 0) JT_CUDA(cudaEventRecord(sc->ext_ev[evi + 1], q));
+      if (P.sampler == 1) {
+        k_wf_shade<1><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+        k_wf_probe<MODE><<<ge, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+        sc->launches += 4;
+      } else {
+        k_wf_shade<2><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+        sc->launches += 3;
+      }
+      k_wf_advance<<<1, 32, 0, q>>>(B, cur[k]);
+      cur[k] = next;
     }
+    st->wf_iterations++;
+    if ((it + 1) % poll_every == 0) {
+      for (int k = 0; k < npipe; k++)
+        if (active[k])
+          JT_CUDA(cudaMemcpyAsync(st->h_counts + k * WF_C_TOTAL, st->wf[k].counts, WF_C_TOTAL * 4, cudaMemcpyDeviceToHost,
+                                  st->pipe_stream[k]));
+      bool any = false;
+      for (int k = 0; k < npipe; k++) {
+        if (!active[k]) continue;
+        JT_CUDA(cudaStreamSynchronize(st->pipe_stream[k]));
+        if (k == 0) {
+          // pipeline 0 stands for all of them in the per-kernel timing (same work per pixel on average)
+          for (int e = 0; e < poll_every; e++) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, sc->ext_ev[2 * e], sc->ext_ev[2 * e + 1]) == cudaSuccess) sc->extend_ms += ms;
+            sc->extend_launches++;
+          }
+        }
+        remaining[k] = st->h_counts[k * WF_C_TOTAL + WF_C_EXT0 + cur[k]];
+        if (remaining[k] == 0) active[k] = false;
+        any = any || active[k];
+      }
+      if (!any) break;
+    }
+  }
+  // later work on the main stream (download, the next range) waits for every pipeline
+  for (int k = 1; k < npipe; k++) {
+    JT_CUDA(cudaEventRecord(st->pipe_done[k], st->pipe_stream[k]));
+    JT_CUDA(cudaStreamWaitEvent(sc->stream, st->pipe_done[k], 0));
   }
   JT_CUDA(cudaGetLastError());
   return JT_OK;

@@ -52,7 +52,8 @@ struct WfBuffers {
   int* q_shade;  // WF_NKEY segments of n
   int* q_probe;
   int* counts;   // WF_C_TOTAL ints
-  int n;         // slots = pixels
+  int n;         // slots of this pipeline
+  int pixel_base;  // slot s renders pixel pixel_base + s (the image may be split over several pipelines)
 };
 
 JT_DEV unsigned lane_id() { return threadIdx.x & 31u; }
@@ -107,10 +108,11 @@ JT_DEV void wf_store_ctl(const WfBuffers& B, int s, const WfPath& p) {
 
 // Start sample `sample` of pixel `s`: RNG draws 0..3, camera ray, unit weight (src/trace.jl:597-608, :286-296).
 JT_DEV void wf_start_sample(const JtDevScene& S, const WfBuffers& B, const DevParams& P, int s, unsigned sample) {
-  Rng rng{jt_rng_key(P.seed, (uint32_t)s, sample), 0u};
+  const int pix = B.pixel_base + s;
+  Rng rng{jt_rng_key(P.seed, (uint32_t)pix, sample), 0u};
   f2 puv = rng.next2();
   f2 luv = rng.next2();
-  int i = s % P.width, j = s / P.width;
+  int i = pix % P.width, j = pix / P.width;
   DRay ray = sample_camera(S.cameras[P.camera], i, j, P.width, P.height, puv, luv, P.tentfilter != 0);
   B.ray0[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
   B.ray1[s] = make_float4(ray.d.y, ray.d.z, 0.0f, 0.0f);
@@ -136,12 +138,13 @@ JT_DEV bool wf_finish_sample(const JtDevScene& S, const WfBuffers& B, const DevS
     r.albedo = f3{0.0f, 0.0f, 0.0f};
     r.normal = f3{0.0f, 0.0f, 0.0f};
     // the camera ray direction (normal AOV of a miss) is a pure function of the RNG stream: recompute
-    Rng rng{jt_rng_key(P.seed, (uint32_t)s, p.sample), 0u};
+    const int pix = B.pixel_base + s;
+    Rng rng{jt_rng_key(P.seed, (uint32_t)pix, p.sample), 0u};
     f2 puv = rng.next2();
     f2 luv = rng.next2();
-    cam_d = sample_camera(S.cameras[P.camera], s % P.width, s / P.width, P.width, P.height, puv, luv, P.tentfilter != 0).d;
+    cam_d = sample_camera(S.cameras[P.camera], pix % P.width, pix / P.width, P.width, P.height, puv, luv, P.tentfilter != 0).d;
   }
-  accumulate_sample(st, P, S.num_environments != 0, s, (int)p.sample, r, cam_d);
+  accumulate_sample(st, P, S.num_environments != 0, B.pixel_base + s, (int)p.sample, r, cam_d);
   (void)paths_done;
   if ((int)p.sample + 1 < sample_end) {
     wf_start_sample(S, B, P, s, p.sample + 1u);
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene
   if (s >= 0) {
     const f3 zero = f3{0.0f, 0.0f, 0.0f};
     WfPath p = wf_load_ctl(B, s);
-    uint64_t rkey = jt_rng_key(P.seed, (uint32_t)s, p.sample);
+    uint64_t rkey = jt_rng_key(P.seed, (uint32_t)(B.pixel_base + s), p.sample);
     Rng rng{rkey, p.draw};
     float4 r0 = B.ray0[s], r1 = B.ray1[s], w4 = B.wgt[s], rad4 = B.rad[s];
     DRay ray{f3{r0.x, r0.y, r0.z}, f3{r0.w, r1.x, r1.y}, JT_RAY_EPS, INFINITY};
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(128, JT_PROBE_MINBLOCKS) k_wf_probe(JtDevScene
     f3 position = f3{r0.x, r0.y, r0.z}, incoming = f3{r0.w, r1.x, r1.y};
     float pl = sample_lights_pdf<MODE>(S, position, incoming, cnt);
     f3 weight = (f3{w4.x, w4.y, w4.z} * f3{fb.x, fb.y, fb.z}) / (0.5f * fb.w + 0.5f * pl);
-    uint64_t rkey = jt_rng_key(P.seed, (uint32_t)s, p.sample);
+    uint64_t rkey = jt_rng_key(P.seed, (uint32_t)(B.pixel_base + s), p.sample);
     bool alive = wf_roulette(weight, p, rkey);
     if (alive && !(p.bounce < P.bounces)) alive = false;
     if (alive) {

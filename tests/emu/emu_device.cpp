@@ -146,7 +146,7 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
   B.ray0 = f4[0].data(); B.ray1 = f4[1].data(); B.hit0 = f4[2].data(); B.wgt = f4[3].data(); B.rad = f4[4].data();
   B.bsdf = f4[5].data(); B.alb = f4[6].data(); B.nrm = f4[7].data(); B.med0 = f4[8].data(); B.med1 = f4[9].data();
   B.ctl = ctl.data(); B.q_ext[0] = q0.data(); B.q_ext[1] = q1.data(); B.q_shade = qs.data(); B.q_probe = qp.data();
-  B.counts = counts.data(); B.n = n;
+  B.counts = counts.data(); B.n = n; B.pixel_base = 0;
   unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   auto run = [&](int threads, auto&& kernel) {
     for (int t = 0; t < threads; t++) { emu_blockIdx.x = (unsigned)t; kernel(); }
