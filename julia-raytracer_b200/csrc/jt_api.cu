@@ -168,7 +168,8 @@ static int scene_create_impl(const jt_scene_desc* d, int device, jt_scene* sc) {
       (rc = upload(sc, staged.envs, &P.environments)) || (rc = upload(sc, staged.lights, &P.lights)) ||
       (rc = upload(sc, staged.cdf, &P.light_cdf)) || (rc = upload(sc, staged.cams, &P.cameras)) ||
       (rc = upload(sc, wide.nodes, &wn)) || (rc = upload(sc, wide.tris, &wt)) ||
-      (rc = upload(sc, staged.tri_rank, &P.tri_rank)) || (rc = upload(sc, staged.inst_rank, &P.inst_rank)))
+      (rc = upload(sc, staged.tri_rank, &P.tri_rank)) || (rc = upload(sc, staged.inst_rank, &P.inst_rank)) ||
+      (rc = upload(sc, staged.inst_bounds, &P.inst_bounds)))
     return rc;
   P.wnodes = (const float4*)wn;
   P.wtris = (const float4*)wt;

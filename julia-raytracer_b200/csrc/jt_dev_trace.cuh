@@ -95,6 +95,17 @@ JT_DEV f3 sample_lights(const JtDevScene& S, f3 position, float rl, float rel, f
   return f3{0.0f, 0.0f, 0.0f};
 }
 
+// Conservative ray / padded-box overlap for t >= 0 (never rejects a ray the instance-space walk could hit).
+JT_DEV bool ray_reaches_box(f3 o, f3 d, float4 lo, float4 hi) {
+  float ix = guarded_rcp(d.x), iy = guarded_rcp(d.y), iz = guarded_rcp(d.z);
+  float ax = (lo.x - o.x) * ix, bx = (hi.x - o.x) * ix;
+  float ay = (lo.y - o.y) * iy, by = (hi.y - o.y) * iy;
+  float az = (lo.z - o.z) * iz, bz = (hi.z - o.z) * iz;
+  float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+  float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+  return t0 <= t1 * 1.00001f + 1e-30f;
+}
+
 // ---- sample_lights_pdf, src/trace.jl:1010-1084 --------------------------------------------------------
 template <int MODE>
 JT_DEV float sample_lights_pdf(const JtDevScene& S, f3 position, f3 direction, PathCounters& cnt) {
@@ -109,6 +120,10 @@ JT_DEV float sample_lights_pdf(const JtDevScene& S, f3 position, f3 direction, P
       float area = __ldg(cdf + L.cdf_len - 1);
       for (int bounce = 0; bounce < 100; bounce++) {
         cnt.light_rays++;
+        // wide mode: skip the BLAS walk when the ray cannot reach the light's padded world box
+        if (MODE == MODE_WIDE &&
+            !ray_reaches_box(next_position, direction, __ldg(S.inst_bounds + 2 * L.instance), __ldg(S.inst_bounds + 2 * L.instance + 1)))
+          break;
         DHit h = intersect_instance<MODE>(S, L.instance, DRay{next_position, direction, JT_RAY_EPS, INFINITY});
         if (h.inst < 0) break;
         ElemRef E = elem_ref(S, I, h.elem);

@@ -111,6 +111,7 @@ struct JtDevScene {
   const float4* wtris;     // 48 B (3 x float4) per triangle record: {p1, elem} {e1, inst} {e2, flags}
   const uint32_t* tri_rank;   // [8][num_wtris]: reference visit rank per ray octant (tie-breaks)
   const uint32_t* inst_rank;  // [8][num_instances]
+  const float4* inst_bounds;  // 2 per instance: padded world-space box {lo.xyz,-} {hi.xyz,-} (probe early-out)
   int32_t num_wtris;
   int32_t wide_root;       // root of the top-level wide BVH
 };
@@ -180,6 +181,7 @@ struct JtStagedScene {
   std::vector<JtInstanceRec> inst_recs;
   JtWideResult wide;
   std::vector<uint32_t> tri_rank, inst_rank;
+  std::vector<float4> inst_bounds;
   std::vector<JtMaterialRec> mats;
   std::vector<JtTextureRec> texs;
   std::vector<float4> texels_f;
@@ -201,6 +203,7 @@ struct JtStagedPointers {
   const JtEnvRec* environments = nullptr; const JtLightRec* lights = nullptr; const float* light_cdf = nullptr;
   const JtCameraRec* cameras = nullptr; const float4* wnodes = nullptr; const float4* wtris = nullptr;
   const uint32_t* tri_rank = nullptr; const uint32_t* inst_rank = nullptr;
+  const float4* inst_bounds = nullptr;
 };
 int jt_stage_scene(const jt_scene_desc* desc, JtStagedScene* out);
 void jt_fill_dev_scene(const JtStagedScene& S, const JtStagedPointers& P, JtDevScene* D);

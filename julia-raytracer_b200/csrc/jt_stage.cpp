@@ -207,6 +207,33 @@ int jt_stage_scene(const jt_scene_desc* d, JtStagedScene* S) {
     R._pad = 0;
   }
 
+  // ---- padded world-space box per instance: lets the light-pdf probes skip instances the ray cannot reach
+  S->inst_bounds.assign(2 * (size_t)d->num_instances, make_float4(0, 0, 0, 0));
+  for (int64_t i = 0; i < d->num_instances; i++) {
+    const JtHostInstance& H = hinst[(size_t)i];
+    const JtHostShape& sh = hshapes[(size_t)H.shape];
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (!sh.ref_nodes.empty()) {
+      const jt_bvh_node& rn = sh.ref_nodes[0];
+      for (int c = 0; c < 8; c++) {
+        float p[3] = {(c & 4) ? rn.bbox_max[0] : rn.bbox_min[0], (c & 2) ? rn.bbox_max[1] : rn.bbox_min[1],
+                      (c & 1) ? rn.bbox_max[2] : rn.bbox_min[2]};
+        for (int k = 0; k < 3; k++) {
+          float w = ((H.frame[k] * p[0] + H.frame[3 + k] * p[1]) + H.frame[6 + k] * p[2]) + H.frame[9 + k];
+          lo[k] = std::fmin(lo[k], w);
+          hi[k] = std::fmax(hi[k], w);
+        }
+      }
+      for (int k = 0; k < 3; k++) {  // generous slack: the probe itself is tested in instance space
+        float pad = 1e-4f * std::fmax(std::fabs(lo[k]), std::fabs(hi[k])) + 1e-5f * (hi[k] - lo[k]) + 1e-30f;
+        lo[k] -= pad;
+        hi[k] += pad;
+      }
+    }
+    S->inst_bounds[2 * (size_t)i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+    S->inst_bounds[2 * (size_t)i + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+  }
+
   // ---- wide BVH ----------------------------------------------------------------------------------------
   std::vector<jt_bvh_node> tlas_nodes(d->bvh.nodes, d->bvh.nodes + d->bvh.num_nodes);
   std::vector<int64_t> tlas_prims(d->bvh.primitives, d->bvh.primitives + d->bvh.num_primitives);
@@ -326,7 +353,7 @@ void jt_fill_dev_scene(const JtStagedScene& S, const JtStagedPointers& P, JtDevS
   D->instances = P.instances; D->materials = P.materials; D->textures = P.textures; D->texels_f = P.texels_f;
   D->texels_b = P.texels_b; D->srgb_lut = P.srgb_lut; D->environments = P.environments; D->lights = P.lights;
   D->light_cdf = P.light_cdf; D->cameras = P.cameras; D->wnodes = P.wnodes; D->wtris = P.wtris;
-  D->tri_rank = P.tri_rank; D->inst_rank = P.inst_rank;
+  D->tri_rank = P.tri_rank; D->inst_rank = P.inst_rank; D->inst_bounds = P.inst_bounds;
   D->tlas_num_nodes = S.tlas_num_nodes; D->num_instances = S.num_instances;
   D->num_environments = S.num_environments; D->num_lights = S.num_lights;
   D->num_wtris = (int32_t)S.wide.tris.size(); D->wide_root = S.wide.top_root;

@@ -33,7 +33,7 @@ EMU_API void* emu_create(const jt_scene_desc* d) {
   P.texels_b = S.texels_b.data(); P.srgb_lut = S.lut.data(); P.environments = S.envs.data();
   P.lights = S.lights.data(); P.light_cdf = S.cdf.data(); P.cameras = S.cams.data();
   P.wnodes = (const float4*)S.wide.nodes.data(); P.wtris = (const float4*)S.wide.tris.data();
-  P.tri_rank = S.tri_rank.data(); P.inst_rank = S.inst_rank.data();
+  P.tri_rank = S.tri_rank.data(); P.inst_rank = S.inst_rank.data(); P.inst_bounds = S.inst_bounds.data();
   jt_fill_dev_scene(S, P, &e->dev);
   return e;
 }
