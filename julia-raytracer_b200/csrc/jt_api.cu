@@ -169,7 +169,7 @@ static int scene_create_impl(const jt_scene_desc* d, int device, jt_scene* sc) {
       (rc = upload(sc, staged.cdf, &P.light_cdf)) || (rc = upload(sc, staged.cams, &P.cameras)) ||
       (rc = upload(sc, wide.nodes, &wn)) || (rc = upload(sc, wide.tris, &wt)) ||
       (rc = upload(sc, staged.tri_rank, &P.tri_rank)) || (rc = upload(sc, staged.inst_rank, &P.inst_rank)) ||
-      (rc = upload(sc, staged.inst_bounds, &P.inst_bounds)))
+      (rc = upload(sc, staged.inst_bounds, &P.inst_bounds)) || (rc = upload(sc, staged.cdf_guide, &P.light_guide)))
     return rc;
   P.wnodes = (const float4*)wn;
   P.wtris = (const float4*)wt;
@@ -694,11 +694,11 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
       }
       if (k == 0) JT_CUDA(cudaEventRecord(sc->ext_ev[evi + 1], q));
       if (P.sampler == 1) {
-        k_wf_shade<1><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+        k_wf_shade<1, MODE><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
         k_wf_probe<MODE><<<ge, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
         sc->launches += 4;
       } else {
-        k_wf_shade<2><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+        k_wf_shade<2, MODE><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
         sc->launches += 3;
       }
       k_wf_advance<<<1, 32, 0, q>>>(B, cur[k]);

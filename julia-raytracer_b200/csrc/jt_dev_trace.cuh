@@ -60,6 +60,32 @@ JT_DEV int sample_discrete(const float* cdf, int n, float r) {  // :33-37, 1-bas
   r = jl_clamp(r * last, 0.0f, last - 0.00001f);
   return jl_clampi(upper_bound(cdf, n, r), 1, n);
 }
+// sample_discrete of a light's CDF: the same bisection, started from the bracket the light's guide table gives
+// for the search key (jt_stage.cpp build_cdf_guide proves the answer lies inside it), so the returned index is
+// the reference's; 17-21 dependent loads become 2 + a few.
+JT_DEV int sample_discrete_light(const JtDevScene& S, const JtLightRec& L, float r) {
+  const float* cdf = S.light_cdf + L.cdf_off;
+  const int n = L.cdf_len;
+  if (L.guide_len == 0) return sample_discrete(cdf, n, r);
+  float last = __ldg(cdf + n - 1);
+  float limit = jl_clamp(r * last, 0.0f, last - 0.00001f);
+  int b = (int)(limit * L.guide_scale);
+  b = b < 0 ? 0 : (b > L.guide_len - 1 ? L.guide_len - 1 : b);
+  const int32_t* G = S.light_guide + L.guide_off;
+  int lo = __ldg(G + b) + 1, hi = __ldg(G + b + 1) + 1;
+  if (hi > n) hi = n;
+  int idx = 0;
+  while (lo <= hi) {
+    int m = (lo + hi) / 2;
+    if (__ldg(cdf + m - 1) > limit) {
+      idx = m;
+      hi = m - 1;
+    } else {
+      lo = m + 1;
+    }
+  }
+  return jl_clampi(idx, 1, n);
+}
 JT_DEV float sample_discrete_pdf(const float* cdf, int idx) {  // :39-40, idx 1-based
   return idx == 1 ? __ldg(cdf) : __ldg(cdf + idx - 1) - __ldg(cdf + idx - 2);
 }
@@ -71,7 +97,7 @@ JT_DEV f3 sample_lights(const JtDevScene& S, f3 position, float rl, float rel, f
   const float* cdf = S.light_cdf + L.cdf_off;
   if (L.instance >= 0) {
     const JtInstanceRec& I = S.instances[L.instance];
-    int element = sample_discrete(cdf, L.cdf_len, rel) - 1;
+    int element = sample_discrete_light(S, L, rel) - 1;
     ElemRef E = elem_ref(S, I, element);
     f2 uv = ruv;
     if (E.sh->kind == 1) {  // sample_triangle, src/sampling.jl:58
@@ -84,7 +110,7 @@ JT_DEV f3 sample_lights(const JtDevScene& S, f3 position, float rl, float rel, f
     const JtEnvRec& En = S.environments[L.environment];
     if (En.emission_tex >= 0) {
       const JtTextureRec T = S.textures[En.emission_tex];
-      int idx = sample_discrete(cdf, L.cdf_len, rel);  // 1-based, used as is (Q7)
+      int idx = sample_discrete_light(S, L, rel);  // 1-based, used as is (Q7)
       float u = ((float)(idx % T.width) + 0.5f) / (float)T.width;
       float v = (float)((((double)idx / (double)T.width) + (double)0.5f) / (double)T.height);
       float up = (u * 2.0f) * JT_PIF, vp = v * JT_PIF;
@@ -107,9 +133,14 @@ JT_DEV bool ray_reaches_box(f3 o, f3 d, float4 lo, float4 hi) {
 }
 
 // ---- sample_lights_pdf, src/trace.jl:1010-1084 --------------------------------------------------------
-template <int MODE>
-JT_DEV float sample_lights_pdf(const JtDevScene& S, f3 position, f3 direction, PathCounters& cnt) {
+// WALK = false is the variant the wide-mode shade kernel runs inline: it evaluates the sum as long as no area
+// light can be reached by the ray (the box early-out below makes those terms exact zeros) and reports
+// *need_walk = true (result unused) as soon as one can -- the slot then goes to the probe kernel, which runs
+// the full WALK = true version. Same expression either way.
+template <int MODE, bool WALK>
+JT_DEV float sample_lights_pdf_impl(const JtDevScene& S, f3 position, f3 direction, PathCounters& cnt, bool* need_walk) {
   float pdf = 0.0f;
+  unsigned probes = 0u;
   for (int li = 0; li < S.num_lights; li++) {
     const JtLightRec L = S.lights[li];
     const float* cdf = S.light_cdf + L.cdf_off;
@@ -117,13 +148,17 @@ JT_DEV float sample_lights_pdf(const JtDevScene& S, f3 position, f3 direction, P
       const JtInstanceRec& I = S.instances[L.instance];
       float lpdf = 0.0f;
       f3 next_position = position;
-      float area = __ldg(cdf + L.cdf_len - 1);
+      float area = WALK ? __ldg(cdf + L.cdf_len - 1) : 0.0f;
       for (int bounce = 0; bounce < 100; bounce++) {
-        cnt.light_rays++;
+        probes++;
         // wide mode: skip the BLAS walk when the ray cannot reach the light's padded world box
         if (MODE == MODE_WIDE &&
             !ray_reaches_box(next_position, direction, __ldg(S.inst_bounds + 2 * L.instance), __ldg(S.inst_bounds + 2 * L.instance + 1)))
           break;
+        if (!WALK) {
+          *need_walk = true;
+          return 0.0f;
+        }
         DHit h = intersect_instance<MODE>(S, L.instance, DRay{next_position, direction, JT_RAY_EPS, INFINITY});
         if (h.inst < 0) break;
         ElemRef E = elem_ref(S, I, h.elem);
@@ -153,7 +188,13 @@ JT_DEV float sample_lights_pdf(const JtDevScene& S, f3 position, f3 direction, P
     }
   }
   pdf *= sample_uniform_pdf(S.num_lights);
+  cnt.light_rays += probes;
   return pdf;
+}
+template <int MODE>
+JT_DEV float sample_lights_pdf(const JtDevScene& S, f3 position, f3 direction, PathCounters& cnt) {
+  bool unused = false;
+  return sample_lights_pdf_impl<MODE, true>(S, position, direction, cnt, &unused);
 }
 
 struct TraceOut {

@@ -266,11 +266,26 @@ JT_DEV bool wf_roulette(f3& weight, WfPath& p, uint64_t key) {
 #ifndef JT_PROBE_MINBLOCKS
 #define JT_PROBE_MINBLOCKS 6
 #endif
-template <int SAMPLER>
+// MODE_WIDE only: when the sampled direction cannot reach any area light's padded box, sample_lights_pdf needs no
+// BLAS walk (every area term is an exact zero), so the MIS weight and the Russian roulette of src/trace.jl:386-397,
+// :455-465 are finished right here and the slot skips the probe kernel's state round trip.
+template <int MODE>
+JT_DEV bool wf_inline_mis(const JtDevScene& S, f3 position, f3 incoming, f3 f, float pdf_bsdf, f3& weight,
+                          PathCounters& cnt) {
+  if (MODE != MODE_WIDE) return false;
+  bool need_walk = false;
+  float pl = sample_lights_pdf_impl<MODE, false>(S, position, incoming, cnt, &need_walk);
+  if (need_walk) return false;
+  weight = (weight * f) / (0.5f * pdf_bsdf + 0.5f * pl);
+  return true;
+}
+
+template <int SAMPLER, int MODE>
 __global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
                                                   int sample_end, unsigned long long* counters) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int key = -1, s = -1;
+  PathCounters cnt{0u, 0u};
   {
     int off = 0;
 #pragma unroll
@@ -372,8 +387,10 @@ __global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene
               } else {
                 f3 f = eval_bsdfcos(material, normal, outgoing, incoming);
                 float pb = sample_bsdfcos_pdf(material, normal, outgoing, incoming);
-                B.bsdf[s] = make_float4(f.x, f.y, f.z, pb);
-                to_probe = true;
+                if (!wf_inline_mis<MODE>(S, position, incoming, f, pb, weight, cnt)) {
+                  B.bsdf[s] = make_float4(f.x, f.y, f.z, pb);
+                  to_probe = true;
+                }
               }
             } else {
               incoming = sample_delta(material, normal, outgoing, rng.next());
@@ -391,7 +408,7 @@ __global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene
             }
             if (alive) {
               ray = DRay{position, incoming, JT_RAY_EPS, INFINITY};
-              if (!to_probe) {  // delta lobe: finish the bounce here
+              if (!to_probe) {  // delta lobe, or MIS weight already applied: finish the bounce here
                 p.draw = rng.draw;
                 alive = wf_roulette(weight, p, rkey);
                 rng.draw = p.draw;
@@ -440,9 +457,16 @@ __global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene
         } else {
           f3 f = eval_scattering(medium, outgoing, incoming);
           float ps = sample_scattering_pdf(medium, outgoing, incoming);
-          B.bsdf[s] = make_float4(f.x, f.y, f.z, ps);
           ray = DRay{position, incoming, JT_RAY_EPS, INFINITY};
-          to_probe = true;
+          if (wf_inline_mis<MODE>(S, position, incoming, f, ps, weight, cnt)) {
+            p.draw = rng.draw;
+            alive = wf_roulette(weight, p, rkey);
+            rng.draw = p.draw;
+            to_extend = alive;
+          } else {
+            B.bsdf[s] = make_float4(f.x, f.y, f.z, ps);
+            to_probe = true;
+          }
         }
       }
     }
@@ -465,6 +489,10 @@ __global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene
   }
   wf_append(B.q_probe, B.counts + WF_C_PROBE, to_probe, s);
   wf_append(B.q_ext[next], B.counts + WF_C_EXT0 + next, to_extend, s);
+  if (SAMPLER == 1 && MODE == MODE_WIDE) {
+    unsigned lr = __reduce_add_sync(0xFFFFFFFFu, cnt.light_rays);
+    if (lane_id() == 0u && lr) atomicAdd(counters + 2, (unsigned long long)lr);
+  }
 }
 
 // ---- probe ---------------------------------------------------------------------------------------------

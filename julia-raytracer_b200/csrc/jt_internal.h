@@ -66,9 +66,14 @@ struct JtEnvRec {  // 64 B
   int32_t emission_tex;
 };
 
-struct JtLightRec {  // 16 B
+struct JtLightRec {  // 32 B
   int32_t instance, environment;
   int32_t cdf_off, cdf_len;
+  // guide table over the CDF's VALUE range (jt_stage.cpp: build_cdf_guide): bucket b = (int)(limit * guide_scale)
+  // brackets upper_bound's answer between guide[b] + 1 and guide[b + 1] + 1. guide_len == 0: no table.
+  int32_t guide_off, guide_len;
+  float guide_scale;
+  int32_t _pad;
 };
 
 struct JtCameraRec {  // 80 B
@@ -105,6 +110,7 @@ struct JtDevScene {
   int32_t num_lights;
   const JtLightRec* lights;
   const float* light_cdf;
+  const int32_t* light_guide;  // guide_len + 1 entries per light that has a table
   const JtCameraRec* cameras;
   // wide (fast) traversal
   const float4* wnodes;    // 80 B (5 x float4) per node
@@ -189,6 +195,7 @@ struct JtStagedScene {
   std::vector<JtEnvRec> envs;
   std::vector<JtLightRec> lights;
   std::vector<float> cdf;
+  std::vector<int32_t> cdf_guide;
   std::vector<JtCameraRec> cams;
   std::vector<float> lut;
   int depth = 0, blas_depth = 0;
@@ -201,9 +208,11 @@ struct JtStagedPointers {
   const JtMaterialRec* materials = nullptr; const JtTextureRec* textures = nullptr;
   const float4* texels_f = nullptr; const uchar4* texels_b = nullptr; const float* srgb_lut = nullptr;
   const JtEnvRec* environments = nullptr; const JtLightRec* lights = nullptr; const float* light_cdf = nullptr;
+  const int32_t* light_guide = nullptr;
   const JtCameraRec* cameras = nullptr; const float4* wnodes = nullptr; const float4* wtris = nullptr;
   const uint32_t* tri_rank = nullptr; const uint32_t* inst_rank = nullptr;
   const float4* inst_bounds = nullptr;
 };
 int jt_stage_scene(const jt_scene_desc* desc, JtStagedScene* out);
+void jt_build_cdf_guide(const float* cdf, int64_t n, JtLightRec* rec, std::vector<int32_t>* guide);
 void jt_fill_dev_scene(const JtStagedScene& S, const JtStagedPointers& P, JtDevScene* D);

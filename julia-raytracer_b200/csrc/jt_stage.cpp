@@ -2,6 +2,7 @@
 // Julia-side conventions (1-based Int64 ids, 40-byte BvhNode, per-shape arrays) into the flat
 // 0-based device layout of jt_internal.h and builds the wide BVH. Pure host code: the CUDA
 // translation unit (jt_api.cu) only uploads what is staged here.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -86,6 +87,41 @@ static int max_wide_depth(const std::vector<JtWideNode>& nodes, int root) {
   return best;
 }
 
+
+// Guide table for sample_discrete (src/sampling.jl:33-56) on a long CDF: the 17-21 dependent loads of the
+// binary search are the hottest line of the shade kernel (profiles/r01/hot_lines_shade_v3.txt).
+// g(x) = clamp((int)(x * scale), 0, K - 1) is monotone in x, so for a search key `limit` in bucket b every
+// entry with g(c_i) < b is <= limit and every entry with g(c_i) > b is > limit: upper_bound's answer
+// 1 + #{c_i <= limit} lies in [guide[b] + 1, guide[b + 1] + 1] with guide[b] = #{i : g(c_i) < b}. The device runs
+// the reference's own bisection on that bracket, so the returned index is identical. Requires a
+// non-decreasing CDF (sequential sums of non-negative weights are); otherwise no table is built.
+void jt_build_cdf_guide(const float* c, int64_t n, JtLightRec* R, std::vector<int32_t>* guide) {
+  R->guide_off = 0;
+  R->guide_len = 0;
+  R->guide_scale = 0.0f;
+  R->_pad = 0;
+  if (n < 64) return;
+  float last = c[n - 1];
+  if (!(last > 0.0f) || !std::isfinite(last)) return;
+  for (int64_t i = 1; i < n; i++)
+    if (!(c[i] >= c[i - 1])) return;
+  if (!(c[0] >= 0.0f)) return;
+  const int K = (int)std::min<int64_t>(n / 4, 1 << 20);
+  const float scale = (float)K / last;
+  if (!std::isfinite(scale) || !std::isfinite(scale * last)) return;
+  auto g = [&](float x) {
+    int b = (int)(x * scale);
+    return std::max(0, std::min(K - 1, b));
+  };
+  R->guide_off = (int32_t)guide->size();
+  R->guide_len = K;
+  R->guide_scale = scale;
+  guide->resize(guide->size() + (size_t)K + 1, 0);
+  int32_t* G = guide->data() + R->guide_off;
+  // histogram of g(c_i), then exclusive prefix sums: G[b] = #{i : g(c_i) < b}
+  for (int64_t i = 0; i < n; i++) G[g(c[i]) + 1]++;
+  for (int b = 1; b <= K; b++) G[b] += G[b - 1];
+}
 
 int jt_stage_scene(const jt_scene_desc* d, JtStagedScene* S) {
   auto& hshapes = S->hshapes; auto& shape_recs = S->shape_recs; auto& positions = S->positions;
@@ -318,6 +354,7 @@ int jt_stage_scene(const jt_scene_desc* d, JtStagedScene* S) {
     R.cdf_off = (int32_t)cdf.size();
     R.cdf_len = (int32_t)l.num_elements;
     cdf.insert(cdf.end(), l.elements_cdf, l.elements_cdf + l.num_elements);
+    jt_build_cdf_guide(l.elements_cdf, l.num_elements, &R, &S->cdf_guide);
   }
   for (int64_t i = 0; i < d->num_cameras; i++) {
     const jt_camera& c = d->cameras[i];
@@ -352,7 +389,7 @@ void jt_fill_dev_scene(const JtStagedScene& S, const JtStagedPointers& P, JtDevS
   D->normals = P.normals; D->texcoords = P.texcoords; D->colors = P.colors; D->elements = P.elements;
   D->instances = P.instances; D->materials = P.materials; D->textures = P.textures; D->texels_f = P.texels_f;
   D->texels_b = P.texels_b; D->srgb_lut = P.srgb_lut; D->environments = P.environments; D->lights = P.lights;
-  D->light_cdf = P.light_cdf; D->cameras = P.cameras; D->wnodes = P.wnodes; D->wtris = P.wtris;
+  D->light_cdf = P.light_cdf; D->light_guide = P.light_guide; D->cameras = P.cameras; D->wnodes = P.wnodes; D->wtris = P.wtris;
   D->tri_rank = P.tri_rank; D->inst_rank = P.inst_rank; D->inst_bounds = P.inst_bounds;
   D->tlas_num_nodes = S.tlas_num_nodes; D->num_instances = S.num_instances;
   D->num_environments = S.num_environments; D->num_lights = S.num_lights;

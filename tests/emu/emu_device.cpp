@@ -31,7 +31,7 @@ EMU_API void* emu_create(const jt_scene_desc* d) {
   P.colors = S.colors.data(); P.elements = S.elements.data(); P.instances = S.inst_recs.data();
   P.materials = S.mats.data(); P.textures = S.texs.data(); P.texels_f = S.texels_f.data();
   P.texels_b = S.texels_b.data(); P.srgb_lut = S.lut.data(); P.environments = S.envs.data();
-  P.lights = S.lights.data(); P.light_cdf = S.cdf.data(); P.cameras = S.cams.data();
+  P.lights = S.lights.data(); P.light_cdf = S.cdf.data(); P.light_guide = S.cdf_guide.data(); P.cameras = S.cams.data();
   P.wnodes = (const float4*)S.wide.nodes.data(); P.wtris = (const float4*)S.wide.tris.data();
   P.tri_rank = S.tri_rank.data(); P.inst_rank = S.inst_rank.data(); P.inst_bounds = S.inst_bounds.data();
   jt_fill_dev_scene(S, P, &e->dev);
@@ -94,6 +94,25 @@ EMU_API void emu_intersect_instance(void* h, const jt_ray* rays, const int64_t* 
     put_hit(out + i, traversal == 1 ? intersect_instance<MODE_REF>(e->dev, (int)inst[i] - 1, r)
                                     : intersect_instance<MODE_WIDE>(e->dev, (int)inst[i] - 1, r));
   }
+}
+
+// sample_discrete through a guide table (sample_discrete_light) next to the plain bisection, for arbitrary CDFs
+EMU_API int emu_sample_discrete(const float* cdf, int64_t n, const float* r, int64_t m, int32_t* plain, int32_t* guided) {
+  JtLightRec L;
+  memset(&L, 0, sizeof(L));
+  std::vector<int32_t> guide;
+  L.cdf_off = 0;
+  L.cdf_len = (int32_t)n;
+  jt_build_cdf_guide(cdf, n, &L, &guide);
+  JtDevScene S;
+  memset(&S, 0, sizeof(S));
+  S.light_cdf = cdf;
+  S.light_guide = guide.data();
+  for (int64_t i = 0; i < m; i++) {
+    plain[i] = sample_discrete(cdf, (int)n, r[i]);
+    guided[i] = sample_discrete_light(S, L, r[i]);
+  }
+  return L.guide_len;
 }
 
 // trace_sample for samples [begin, end) of every pixel into host accumulators (float4 image/albedo/normal, int hits)
@@ -161,12 +180,13 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
     int ns = 0;
     for (int k = 0; k < WF_NKEY; k++) ns += (counts[WF_C_SHADE + k] + 31) & ~31;
     if (P.sampler == 1) {
-      run(ns, [&] { k_wf_shade<1>(e->dev, B, st, P, next, end, cnt); });
+      if (p->traversal == 1) run(ns, [&] { k_wf_shade<1, MODE_REF>(e->dev, B, st, P, next, end, cnt); });
+      else run(ns, [&] { k_wf_shade<1, MODE_WIDE>(e->dev, B, st, P, next, end, cnt); });
       int np = counts[WF_C_PROBE];
       if (p->traversal == 1) run(np, [&] { k_wf_probe<MODE_REF>(e->dev, B, st, P, next, end, cnt); });
       else run(np, [&] { k_wf_probe<MODE_WIDE>(e->dev, B, st, P, next, end, cnt); });
     } else {
-      run(ns, [&] { k_wf_shade<2>(e->dev, B, st, P, next, end, cnt); });
+      run(ns, [&] { k_wf_shade<2, MODE_REF>(e->dev, B, st, P, next, end, cnt); });
     }
     emu_blockIdx.x = 0;
     k_wf_advance(B, cur);

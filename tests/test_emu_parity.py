@@ -82,3 +82,47 @@ def test_fixed_sample_set_images(pair, name, sampler, extra, traversal, wavefron
     else:  # wide mode: identical except where a ray falls in the residual class (rate <= 1e-4 per ray)
         differing = np.abs(img - ref["image"]).max(axis=-1) > 1e-4
         assert differing.mean() <= 2e-3, differing.mean()
+
+
+@pytest.mark.parametrize("name,sampler,extra", CASES)
+def test_wide_wavefront_equals_wide_megakernel(pair, name, sampler, extra):
+    """Same traversal on both sides, so there is no residual-class slack: the wavefront reorganisation (queues,
+    MIS weights finished inside the shade kernel when no light walk is needed, CDF guide tables) must reproduce the
+    per-thread integrator bit for bit, ray counters included."""
+    o, e = pair(name)
+    p = orc.make_params(resolution=64, samples=3, batch=3, sampler=sampler, traversal=0, seed=23, **extra)
+    w, h = o.make_state(p)
+    a = e.trace(p, w, h, 0, 3, wavefront=False)
+    b = e.trace(p, w, h, 0, 3, wavefront=True)
+    for k in ("image", "albedo", "normal", "hits"):
+        assert np.array_equal(a[k], b[k]), k
+    assert (a["scene_rays"], a["light_rays"]) == (b["scene_rays"], b["light_rays"])
+
+
+def test_cdf_guide_table_returns_the_reference_index():
+    """sample_discrete_light (guide-table bracket + the reference bisection) against the plain bisection of
+    src/sampling.jl:33-56 on adversarial CDFs: plateaus, duplicates, huge and tiny totals, r at the clamp edges."""
+    import ctypes as C
+    L = emu.lib()
+    L.emu_sample_discrete.restype = C.c_int
+    L.emu_sample_discrete.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(3)
+    cases = []
+    for n in (64, 65, 1000, 131072):
+        w = rng.random(n).astype(np.float32)
+        cases.append(w)                                                    # generic
+        cases.append(np.where(rng.random(n) < 0.7, 0, w).astype(np.float32))  # long plateaus
+        cases.append((w * np.float32(1e-9)).astype(np.float32))             # total below the 1e-5 clamp offset
+        cases.append((w * np.float32(1e12)).astype(np.float32))
+        cases.append(np.sin(np.pi * (np.arange(n) // 8 + 0.5) / (n // 8 + 1)).astype(np.float32))  # sky-like rows
+    used = 0
+    for w in cases:
+        cdf = np.cumsum(w, dtype=np.float32)  # sequential Float32 sums, like make_trace_lights
+        r = np.concatenate([rng.random(20000).astype(np.float32), np.float32([0, 1e-8, 0.5, 0.99999994]),
+                            (cdf[rng.integers(0, len(cdf), 2000)] / cdf[-1]).astype(np.float32)])
+        plain = np.zeros(len(r), np.int32)
+        guided = np.zeros(len(r), np.int32)
+        k = L.emu_sample_discrete(cdf.ctypes.data, len(cdf), r.ctypes.data, len(r), plain.ctypes.data, guided.ctypes.data)
+        used += k > 0
+        assert np.array_equal(plain, guided)
+    assert used >= len(cases) // 2  # the table was really in play
