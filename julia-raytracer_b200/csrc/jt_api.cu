@@ -84,7 +84,8 @@ struct jt_state {
   cudaStream_t pipe_stream[JT_MAX_PIPES] = {};
   cudaEvent_t pipe_done[JT_MAX_PIPES] = {};
   std::vector<void*> wf_allocs;
-  int* h_counts = nullptr;  // pinned mirror of the pipelines' counters (WF_C_TOTAL ints each)
+  int* h_counts = nullptr;  // pinned mirror of the pipelines' counters (WF_C_TOTAL ints each), double-buffered
+  cudaEvent_t poll_ev[2][JT_MAX_PIPES] = {};
   // download staging (allocated on first download)
   void* d_pack = nullptr;
   void* h_pack = nullptr;
@@ -192,6 +193,7 @@ static int scene_create_impl(const jt_scene_desc* d, int device, jt_scene* sc) {
   sc->stats.total_device_bytes = sc->device_bytes;
   sc->stats._reserved[0] = staged.depth;
   sc->stats._reserved[1] = staged.blas_depth;
+  sc->stats._reserved[2] = wide.flattened_instances;
   return JT_OK;
 }
 
@@ -494,6 +496,9 @@ extern "C" void jt_state_destroy(jt_state* st) {
     if (st->pipe_stream[k]) cudaStreamDestroy(st->pipe_stream[k]);
   for (int k = 0; k < JT_MAX_PIPES; k++)
     if (st->pipe_done[k]) cudaEventDestroy(st->pipe_done[k]);
+  for (int k = 0; k < JT_MAX_PIPES; k++)
+    for (int b = 0; b < 2; b++)
+      if (st->poll_ev[b][k]) cudaEventDestroy(st->poll_ev[b][k]);
   if (st->h_counts) cudaFreeHost(st->h_counts);
   if (st->d_pack) cudaFree(st->d_pack);
   if (st->h_pack) cudaFreeHost(st->h_pack);
@@ -642,8 +647,10 @@ static int wf_prepare(jt_scene* sc, jt_state* st) {
     st->pipe_stream[k] = sc->stream;
     if (k > 0) JT_CUDA(cudaStreamCreateWithFlags(&st->pipe_stream[k], cudaStreamNonBlocking));
     JT_CUDA(cudaEventCreateWithFlags(&st->pipe_done[k], cudaEventDisableTiming));
+    JT_CUDA(cudaEventCreateWithFlags(&st->poll_ev[0][k], cudaEventDisableTiming));
+    JT_CUDA(cudaEventCreateWithFlags(&st->poll_ev[1][k], cudaEventDisableTiming));
   }
-  JT_CUDA(cudaHostAlloc((void**)&st->h_counts, JT_MAX_PIPES * WF_C_TOTAL * 4, cudaHostAllocDefault));
+  JT_CUDA(cudaHostAlloc((void**)&st->h_counts, 2 * JT_MAX_PIPES * WF_C_TOTAL * 4, cudaHostAllocDefault));
   st->wf_ready = true;
   return JT_OK;
 }
@@ -657,7 +664,8 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
   int rc = wf_prepare(sc, st);
   if (rc) return rc;
   const int npipe = st->npipe;
-  const int poll_every = 4;
+  constexpr int poll_every = 4;
+  static_assert(poll_every % 2 == 0 && 4 * poll_every <= 16, "poll_every: even (queue parity at every poll) and within ext_ev");
   int cur[JT_MAX_PIPES], remaining[JT_MAX_PIPES];
   bool active[JT_MAX_PIPES];
   // the other pipelines start after everything already enqueued on the main stream
@@ -675,58 +683,89 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
   }
   const int pdiv = getenv("JT_PGRID_DIV") ? atoi(getenv("JT_PGRID_DIV")) : 1;
   const unsigned pgrid = std::max(1u, persist_grid(sc) / (unsigned)std::max(1, pdiv));
-  for (int it = 0;; it++) {
-    for (int k = 0; k < npipe; k++) {
-      if (!active[k]) continue;
-      WfBuffers& B = st->wf[k];
-      cudaStream_t q = st->pipe_stream[k];
-      const int next = cur[k] ^ 1;
-      // grids sized from the last polled queue length (an upper bound until the next poll: queues only
-      // shrink, because every slot appears at most once per iteration)
-      unsigned ge = (unsigned)((remaining[k] + 127) / 128), gs = (unsigned)((remaining[k] + 32 * WF_NKEY + 127) / 128);
-      const int evi = 2 * (it % poll_every);
-      if (k == 0) JT_CUDA(cudaEventRecord(sc->ext_ev[evi], q));
-      if (MODE == MODE_WIDE) {
-        unsigned gp = std::min<unsigned>((unsigned)((remaining[k] + JT_PERSIST_BLOCK - 1) / JT_PERSIST_BLOCK), pgrid);
-        k_wf_extend_persist<<<gp, JT_PERSIST_BLOCK, 0, q>>>(sc->dev, B, cur[k], sc->d_counters);
-      } else {
-        k_wf_extend<MODE><<<ge, 128, 0, q>>>(sc->dev, B, cur[k], sc->d_counters);
-      }
-      if (k == 0) JT_CUDA(cudaEventRecord(sc->ext_ev[evi + 1], q));
-      if (P.sampler == 1) {
-        k_wf_shade<1, MODE><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
-        k_wf_probe<MODE><<<ge, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
-        sc->launches += 4;
-      } else {
-        k_wf_shade<2, MODE><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
-        sc->launches += 3;
-      }
-      k_wf_advance<<<1, 32, 0, q>>>(B, cur[k]);
-      cur[k] = next;
-    }
-    st->wf_iterations++;
-    if ((it + 1) % poll_every == 0) {
-      for (int k = 0; k < npipe; k++)
-        if (active[k])
-          JT_CUDA(cudaMemcpyAsync(st->h_counts + k * WF_C_TOTAL, st->wf[k].counts, WF_C_TOTAL * 4, cudaMemcpyDeviceToHost,
-                                  st->pipe_stream[k]));
-      bool any = false;
+  // One batch = poll_every iterations of every active pipeline, followed by an async copy of the queue counters.
+  // The host enqueues batch j + 1 BEFORE it waits for the counters of batch j, so the GPU never drains while the
+  // host looks at queue lengths; the price is one batch of empty launches after a pipeline has run dry.
+  auto enqueue_batch = [&](int batch) -> int {
+    for (int sub = 0; sub < poll_every; sub++) {
+      const int it = batch * poll_every + sub;
       for (int k = 0; k < npipe; k++) {
         if (!active[k]) continue;
-        JT_CUDA(cudaStreamSynchronize(st->pipe_stream[k]));
-        if (k == 0) {
-          // pipeline 0 stands for all of them in the per-kernel timing (same work per pixel on average)
-          for (int e = 0; e < poll_every; e++) {
-            float ms = 0.0f;
-            if (cudaEventElapsedTime(&ms, sc->ext_ev[2 * e], sc->ext_ev[2 * e + 1]) == cudaSuccess) sc->extend_ms += ms;
-            sc->extend_launches++;
-          }
+        WfBuffers& B = st->wf[k];
+        cudaStream_t q = st->pipe_stream[k];
+        const int next = cur[k] ^ 1;
+        // grids sized from the last polled queue length (an upper bound: queues only shrink, because every slot
+        // appears at most once per iteration)
+        unsigned ge = (unsigned)((remaining[k] + 127) / 128), gs = (unsigned)((remaining[k] + 32 * WF_NKEY + 127) / 128);
+        const int evi = 2 * (it % (2 * poll_every));
+        if (k == 0) JT_CUDA(cudaEventRecord(sc->ext_ev[evi], q));
+        if (MODE == MODE_WIDE) {
+          unsigned gp = std::min<unsigned>((unsigned)((remaining[k] + JT_PERSIST_BLOCK - 1) / JT_PERSIST_BLOCK), pgrid);
+          k_wf_extend_persist<<<gp, JT_PERSIST_BLOCK, 0, q>>>(sc->dev, B, cur[k], sc->d_counters);
+        } else {
+          k_wf_extend<MODE><<<ge, 128, 0, q>>>(sc->dev, B, cur[k], sc->d_counters);
         }
-        remaining[k] = st->h_counts[k * WF_C_TOTAL + WF_C_EXT0 + cur[k]];
-        if (remaining[k] == 0) active[k] = false;
-        any = any || active[k];
+        if (k == 0) JT_CUDA(cudaEventRecord(sc->ext_ev[evi + 1], q));
+        if (P.sampler == 1) {
+          k_wf_shade<1, MODE><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+          k_wf_probe<MODE><<<ge, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+          sc->launches += 4;
+        } else {
+          k_wf_shade<2, MODE><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+          sc->launches += 3;
+        }
+        k_wf_advance<<<1, 32, 0, q>>>(B, cur[k]);
+        cur[k] = next;
       }
-      if (!any) break;
+      st->wf_iterations++;
+    }
+    int* hc = st->h_counts + (size_t)(batch & 1) * JT_MAX_PIPES * WF_C_TOTAL;
+    for (int k = 0; k < npipe; k++) {
+      if (!active[k]) continue;
+      JT_CUDA(cudaMemcpyAsync(hc + k * WF_C_TOTAL, st->wf[k].counts, WF_C_TOTAL * 4, cudaMemcpyDeviceToHost, st->pipe_stream[k]));
+      JT_CUDA(cudaEventRecord(st->poll_ev[batch & 1][k], st->pipe_stream[k]));
+    }
+    return JT_OK;
+  };
+  // returns through *any whether some pipeline still has queued rays after `batch`
+  auto collect_batch = [&](int batch, bool polled[JT_MAX_PIPES], bool* any) -> int {
+    const int* hc = st->h_counts + (size_t)(batch & 1) * JT_MAX_PIPES * WF_C_TOTAL;
+    *any = false;
+    for (int k = 0; k < npipe; k++) {
+      if (!polled[k]) continue;
+      JT_CUDA(cudaEventSynchronize(st->poll_ev[batch & 1][k]));
+      if (k == 0) {
+        // pipeline 0 stands for all of them in the per-kernel timing (same work per pixel on average)
+        for (int sub = 0; sub < poll_every; sub++) {
+          const int evi = 2 * ((batch * poll_every + sub) % (2 * poll_every));
+          float ms = 0.0f;
+          if (cudaEventElapsedTime(&ms, sc->ext_ev[evi], sc->ext_ev[evi + 1]) == cudaSuccess) sc->extend_ms += ms;
+          sc->extend_launches++;
+        }
+      }
+      // poll_every is even, so cur[k] is the same queue at every poll
+      remaining[k] = std::min(remaining[k], hc[k * WF_C_TOTAL + WF_C_EXT0 + cur[k]]);
+      if (remaining[k] == 0) active[k] = false;
+      *any = *any || active[k];
+    }
+    return JT_OK;
+  };
+  {
+    bool polled[2][JT_MAX_PIPES];
+    int rc2;
+    for (int k = 0; k < JT_MAX_PIPES; k++) polled[0][k] = polled[1][k] = false;
+    for (int k = 0; k < npipe; k++) polled[0][k] = active[k];
+    if ((rc2 = enqueue_batch(0))) return rc2;
+    for (int batch = 1;; batch++) {
+      for (int k = 0; k < npipe; k++) polled[batch & 1][k] = active[k];
+      if ((rc2 = enqueue_batch(batch))) return rc2;
+      bool any = false;
+      if ((rc2 = collect_batch(batch - 1, polled[(batch - 1) & 1], &any))) return rc2;
+      if (!any) {
+        // the batch just enqueued ran on empty queues; drain its polls so the events / staging can be reused
+        if ((rc2 = collect_batch(batch, polled[batch & 1], &any))) return rc2;
+        break;
+      }
     }
   }
   // later work on the main stream (download, the next range) waits for every pipeline

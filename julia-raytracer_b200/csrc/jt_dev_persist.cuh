@@ -94,18 +94,22 @@ JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, uint2* stack, 
           L.cur_inst = inst;
           const JtInstanceRec& I = S.instances[inst];
           wide_ray_setup(L.R, xform_point(I.inv, L.wo), xform_vector(I.inv, L.wd));
-          L.ngroup = make_uint2((uint32_t)S.shapes[I.shape].wide_root, 0x80000000u);
+          const int entry = __float_as_int(r0.w);  // braided sub-tree of the BLAS, or -1: the whole shape
+          L.ngroup = make_uint2((uint32_t)(entry >= 0 ? entry : S.shapes[I.shape].wide_root), 0x80000000u);
           L.tgroup = make_uint2(0u, 0u);
         } else {
           float t, u, v;
-          if (tri_test(L.R.o, L.R.d, L.tmin, L.best_t, f3{r0.x, r0.y, r0.z}, f3{r1.x, r1.y, r1.z},
+          f3 to = L.R.o, td = L.R.d;
+          uint32_t local_oct = L.R.rank_oct;
+          if (flags & 0x200u) flat_ray(S, __float_as_int(r1.w), L.wo, L.wd, to, td, local_oct);
+          if (tri_test(to, td, L.tmin, L.best_t, f3{r0.x, r0.y, r0.z}, f3{r1.x, r1.y, r1.z},
                        f3{r2.x, r2.y, r2.z}, &t, &u, &v)) {
             int inst = L.cur_inst >= 0 ? L.cur_inst : __float_as_int(r1.w);
             if (flags & 1u) {
               u = 1.0f - u;
               v = 1.0f - v;
             }
-            wide_accept(S, L.best, t, u, v, inst, __float_as_int(r0.w), (int)wtri, L.world_oct, L.R.rank_oct);
+            wide_accept(S, L.best, t, u, v, inst, __float_as_int(r0.w), (int)wtri, L.world_oct, local_oct);
             L.best_t = L.best.t;
           }
         }

@@ -310,6 +310,17 @@ JT_DEV void wide_accept(const JtDevScene& S, WideBest& B, float t, float u, floa
   B.t = t; B.u = u; B.v = v; B.inst = inst; B.elem = elem; B.wtri = wtri;
 }
 
+// Leaf record of a FLATTENED instance (flags bit 9): its triangle is stored in instance space, so the world ray is
+// taken into that space exactly as intersect_scene_bvh does per instance visit (transform_ray with the precomputed
+// inverse(frame, true), src/bvh.jl:345-348) and the reference's own leaf arithmetic runs unchanged.
+JT_DEV void flat_ray(const JtDevScene& S, int inst, f3 wo, f3 wd, f3& o, f3& d, uint32_t& local_oct) {
+  JT_COUNT(wide_xforms);
+  const JtInstanceRec& I = S.instances[inst];
+  o = xform_point(I.inv, wo);
+  d = xform_vector(I.inv, wd);
+  local_oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+}
+
 // Shared traversal core. `root` is a wide node index; when `single_inst` >= 0 the walk starts
 // inside that instance's BLAS with the ray already in instance space (intersect_instance_bvh).
 JT_DEV void wide_walk(const JtDevScene& S, uint32_t root, f3 o, f3 d, float tmin, float tmax, int single_inst,
@@ -356,19 +367,23 @@ JT_DEV void wide_walk(const JtDevScene& S, uint32_t root, f3 o, f3 d, float tmin
         cur_inst = inst;
         const JtInstanceRec& I = S.instances[inst];
         wide_ray_setup(R, xform_point(I.inv, Rworld.o), xform_vector(I.inv, Rworld.d));
-        ngroup = make_uint2((uint32_t)S.shapes[I.shape].wide_root, 0x80000000u);
+        const int entry = __float_as_int(r0.w);  // braided sub-tree of the BLAS, or -1: the whole shape
+        ngroup = make_uint2((uint32_t)(entry >= 0 ? entry : S.shapes[I.shape].wide_root), 0x80000000u);
         tgroup = make_uint2(0u, 0u);
         break;
       }
       float t, u, v;
-      if (tri_test(R.o, R.d, tmin, best_t, f3{r0.x, r0.y, r0.z}, f3{r1.x, r1.y, r1.z}, f3{r2.x, r2.y, r2.z}, &t,
+      f3 to = R.o, td = R.d;
+      uint32_t local_oct = R.rank_oct;
+      if (flags & 0x200u) flat_ray(S, __float_as_int(r1.w), Rworld.o, Rworld.d, to, td, local_oct);
+      if (tri_test(to, td, tmin, best_t, f3{r0.x, r0.y, r0.z}, f3{r1.x, r1.y, r1.z}, f3{r2.x, r2.y, r2.z}, &t,
                    &u, &v)) {
         int inst = cur_inst >= 0 ? cur_inst : __float_as_int(r1.w);
         if (flags & 1u) {
           u = 1.0f - u;
           v = 1.0f - v;
         }
-        wide_accept(S, B, t, u, v, inst, __float_as_int(r0.w), (int)wtri, world_oct, R.rank_oct);
+        wide_accept(S, B, t, u, v, inst, __float_as_int(r0.w), (int)wtri, world_oct, local_oct);
         best_t = B.t;
       }
     }

@@ -141,7 +141,8 @@ struct JtWideTri {  // 48 B
   float e1[3];
   int32_t instance;  // 0-based instance id for inlined geometry, -1 inside an instanced BLAS
   float e2[3];
-  uint32_t flags;    // bit0: second half of a quad (uv -> 1-uv); bits 8..: leaf-kind (1 = instance leaf)
+  uint32_t flags;    // bit0: second half of a quad (uv -> 1-uv); bit8: instance leaf (enter the BLAS);
+                     // bit9: triangle of a flattened instance (test in instance space: transform the ray first)
 };
 static_assert(sizeof(JtWideTri) == 48, "wide tri must be 48 bytes");
 
@@ -167,7 +168,7 @@ struct JtWideResult {
   std::vector<uint32_t> inst_rank[8];  // per octant, indexed by instance
   std::vector<int32_t> shape_root;     // per shape: root node of its BLAS or -1
   int32_t top_root = -1;
-  int64_t inlined_instances = 0, instanced_instances = 0;
+  int64_t inlined_instances = 0, instanced_instances = 0, flattened_instances = 0;
 };
 // Returns 0 or a negative jt_status (message set).
 int jt_build_wide(const std::vector<JtHostShape>& shapes, const std::vector<JtHostInstance>& instances,

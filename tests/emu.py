@@ -49,9 +49,9 @@ class Emu:
             self.h = None
 
     def stats(self):
-        out = np.zeros(6, np.int64)
+        out = np.zeros(8, np.int64)
         self.L.emu_stats(self.h, out.ctypes.data)
-        return dict(zip(["wide_nodes", "wide_tris", "inlined", "instanced", "depth_top", "depth_blas"], map(int, out)))
+        return dict(zip(["wide_nodes", "wide_tris", "inlined", "instanced", "depth_top", "depth_blas", "flattened"], map(int, out)))
 
     def intersect(self, rays, traversal=0):
         rays = np.ascontiguousarray(rays, dtype=A.RAY_DTYPE)
@@ -83,6 +83,6 @@ class Emu:
 
 
 def wide_counts(reset=True):
-    out = np.zeros(3, np.uint64)
+    out = np.zeros(4, np.uint64)
     lib().emu_wide_counts(out.ctypes.data, int(reset))
-    return dict(nodes=int(out[0]), prims=int(out[1]), instances=int(out[2]))
+    return dict(nodes=int(out[0]), prims=int(out[1]), instances=int(out[2]), xforms=int(out[3]))

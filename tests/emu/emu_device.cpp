@@ -6,6 +6,8 @@
 #include "../../julia-raytracer_b200/csrc/jt_dev_wavefront.cuh"
 
 #include <omp.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 
 struct Emu {
@@ -45,6 +47,7 @@ EMU_API void emu_stats(void* h, int64_t* out) {
   out[1] = (int64_t)e->staged.wide.tris.size();
   out[2] = e->staged.wide.inlined_instances;
   out[3] = e->staged.wide.instanced_instances;
+  out[6] = e->staged.wide.flattened_instances;
   out[4] = e->staged.depth;
   out[5] = e->staged.blas_depth;
 }
@@ -67,15 +70,15 @@ static DHit persist_one(const JtDevScene& S, const DRay& r) {
   persist_traverse(S, L, stack, live, false);
   return DHit{L.best.t, L.best.u, L.best.v, L.best.inst, L.best.elem};
 }
-static unsigned long long g_wide_counts[3] = {0, 0, 0};
+static unsigned long long g_wide_counts[4] = {0, 0, 0, 0};
 EMU_API void emu_wide_counts(unsigned long long* out, int reset) {
-  for (int k = 0; k < 3; k++) { out[k] = g_wide_counts[k]; if (reset) g_wide_counts[k] = 0; }
+  for (int k = 0; k < 4; k++) { out[k] = g_wide_counts[k]; if (reset) g_wide_counts[k] = 0; }
 }
 EMU_API void emu_intersect(void* h, const jt_ray* rays, int64_t n, int traversal, jt_hit* out) {
   Emu* e = (Emu*)h;
 #pragma omp parallel
   {
-    jt_emu_counts = jt_emu_counts_t{0, 0, 0};
+    jt_emu_counts = jt_emu_counts_t{0, 0, 0, 0};
 #pragma omp for schedule(dynamic, 1024)
     for (int64_t i = 0; i < n; i++) {
       DRay r{f3{rays[i].o[0], rays[i].o[1], rays[i].o[2]}, f3{rays[i].d[0], rays[i].d[1], rays[i].d[2]}, rays[i].tmin, rays[i].tmax};
@@ -83,7 +86,7 @@ EMU_API void emu_intersect(void* h, const jt_ray* rays, int64_t n, int traversal
                                       : (traversal == 3 ? persist_one(e->dev, r) : intersect_scene<MODE_WIDE>(e->dev, r)));
     }
 #pragma omp critical
-    { g_wide_counts[0] += jt_emu_counts.wide_nodes; g_wide_counts[1] += jt_emu_counts.wide_prims; g_wide_counts[2] += jt_emu_counts.wide_instances; }
+    { g_wide_counts[0] += jt_emu_counts.wide_nodes; g_wide_counts[1] += jt_emu_counts.wide_prims; g_wide_counts[2] += jt_emu_counts.wide_instances; g_wide_counts[3] += jt_emu_counts.wide_xforms; }
   }
 }
 EMU_API void emu_intersect_instance(void* h, const jt_ray* rays, const int64_t* inst, int64_t n, int traversal, jt_hit* out) {
@@ -183,6 +186,8 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
       if (p->traversal == 1) run(ns, [&] { k_wf_shade<1, MODE_REF>(e->dev, B, st, P, next, end, cnt); });
       else run(ns, [&] { k_wf_shade<1, MODE_WIDE>(e->dev, B, st, P, next, end, cnt); });
       int np = counts[WF_C_PROBE];
+      cnt[5] += (unsigned long long)np;  // slots that still needed the probe kernel
+      cnt[6] += (unsigned long long)ns;
       if (p->traversal == 1) run(np, [&] { k_wf_probe<MODE_REF>(e->dev, B, st, P, next, end, cnt); });
       else run(np, [&] { k_wf_probe<MODE_WIDE>(e->dev, B, st, P, next, end, cnt); });
     } else {
@@ -194,6 +199,7 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
     iterations++;
   }
   if (counters) { counters[0] += cnt[1]; counters[1] += cnt[2]; counters[2] += cnt[0]; }
+  if (getenv("JT_EMU_VERBOSE")) fprintf(stderr, "emu wavefront: %d iterations, shade slots %llu, probe-kernel slots %llu, light probes %llu\n", iterations, cnt[6], cnt[5], cnt[2]);
   return iterations;
 }
 }

@@ -40,8 +40,8 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 #endif
 
 #define JT_EMU_COUNT 1
-struct jt_emu_counts_t { unsigned long long wide_nodes, wide_prims, wide_instances; };
-static thread_local jt_emu_counts_t jt_emu_counts = {0, 0, 0};
+struct jt_emu_counts_t { unsigned long long wide_nodes, wide_prims, wide_instances, wide_xforms; };
+static thread_local jt_emu_counts_t jt_emu_counts = {0, 0, 0, 0};
 
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
   unsigned long long v = ((unsigned long long)y << 32) | x;

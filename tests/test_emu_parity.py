@@ -126,3 +126,37 @@ def test_cdf_guide_table_returns_the_reference_index():
         used += k > 0
         assert np.array_equal(plain, guided)
     assert used >= len(cases) // 2  # the table was really in play
+
+
+@pytest.mark.parametrize("name", ["features1", "classroom", "synthetic_all"])
+@pytest.mark.parametrize("braid", [1, 16])
+def test_braided_and_flattened_instances_return_the_same_hits(scenes, name, braid, monkeypatch):
+    """Instances with a non-identity frame can be opened into the top-level tree (JT_BRAID_MAX = 1: every triangle
+    becomes a flattened record tested in instance space; 16: entry records at BLAS sub-trees of <= 16 triangles).
+    The topology only decides which boxes are visited: hits must equal the two-level walk's bit for bit and obey the
+    wide-vs-reference contract."""
+    sc, b, lights = scenes(name)
+    o = orc.Oracle(sc, b, lights)
+    monkeypatch.setenv("JT_BRAID_MAX", "0")
+    plain = emu.Emu(sc, b, lights)
+    monkeypatch.setenv("JT_BRAID_MAX", str(braid))
+    monkeypatch.setenv("JT_BRAID_MIN_INSTANCES", "1")
+    opened = emu.Emu(sc, b, lights)
+    assert plain.stats()["flattened"] == 0 and opened.stats()["flattened"] > 0
+    p = orc.make_params(resolution=128)
+    w, h = o.make_state(p)
+    cur = raygen.camera_rays(o, p, w, h, 20000, seed=31)
+    rays = [cur]
+    for g in range(2):
+        cur = raygen.secondary_rays(cur, o.intersect(cur), seed=32 + g)
+        rays.append(cur)
+    rays = np.concatenate(rays)
+    ref = o.intersect(rays)
+    for mode in (0, 3):  # plain wide walk, persistent-warp state machine
+        a, c = plain.intersect(rays, mode), opened.intersect(rays, mode)
+        assert np.array_equal(a.view(np.uint8), c.view(np.uint8))
+        raygen.check_wide_vs_reference(c, ref)
+    pp = orc.make_params(resolution=48, samples=2, batch=2, sampler=1, traversal=0, seed=5)
+    w, h = o.make_state(pp)
+    x, y = plain.trace(pp, w, h, 0, 2, wavefront=True), opened.trace(pp, w, h, 0, 2, wavefront=True)
+    assert np.array_equal(x["image"], y["image"]) and np.array_equal(x["hits"], y["hits"])

@@ -65,7 +65,7 @@ for key in list(out):
     emu.wide_counts()
     e.intersect(rays, 0)
     wc = emu.wide_counts()
-    out[key]["wide_bytes_per_scene_ray"] = 56 + (80 * wc["nodes"] + 48 * wc["prims"] + 112 * wc["instances"]) / len(rays)
+    out[key]["wide_bytes_per_scene_ray"] = 56 + (80 * wc["nodes"] + 48 * wc["prims"] + 112 * wc["instances"] + 48 * wc["xforms"]) / len(rays)
     out[key]["wide_nodes_per_scene_ray"] = wc["nodes"] / len(rays)
     out[key]["wide_prims_per_scene_ray"] = wc["prims"] / len(rays)
     print(key, "as implemented:", round(out[key]["wide_bytes_per_scene_ray"]), "B per scene ray", flush=True)
