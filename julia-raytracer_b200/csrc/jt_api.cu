@@ -636,14 +636,14 @@ static int wf_prepare(jt_scene* sc, jt_state* st) {
     B.pixel_base = (int)base;
     base += n;
     int rc;
-    if ((rc = alloc((void**)&B.ray0, n * 16)) || (rc = alloc((void**)&B.ray1, n * 16)) || (rc = alloc((void**)&B.hit0, n * 16)) ||
-        (rc = alloc((void**)&B.wgt, n * 16)) || (rc = alloc((void**)&B.rad, n * 16)) || (rc = alloc((void**)&B.bsdf, n * 16)) ||
-        (rc = alloc((void**)&B.alb, n * 16)) || (rc = alloc((void**)&B.nrm, n * 16)) || (rc = alloc((void**)&B.med0, n * 16)) ||
-        (rc = alloc((void**)&B.med1, n * 16)) || (rc = alloc((void**)&B.ctl, n * 16)) ||
+    float4 *ga = nullptr, *gb = nullptr, *gc = nullptr, *gd = nullptr;
+    if ((rc = alloc((void**)&ga, n * 64)) || (rc = alloc((void**)&gb, n * 64)) || (rc = alloc((void**)&gc, n * 32)) ||
+        (rc = alloc((void**)&gd, n * 32)) ||
         (rc = alloc((void**)&B.q_ext[0], n * 4)) || (rc = alloc((void**)&B.q_ext[1], n * 4)) ||
         (rc = alloc((void**)&B.q_shade, n * 4 * WF_NKEY)) || (rc = alloc((void**)&B.q_probe, n * 4)) ||
         (rc = alloc((void**)&B.counts, WF_C_TOTAL * 4)))
       return rc;
+    B.bind(ga, gb, gc, gd);
     st->pipe_stream[k] = sc->stream;
     if (k > 0) JT_CUDA(cudaStreamCreateWithFlags(&st->pipe_stream[k], cudaStreamNonBlocking));
     JT_CUDA(cudaEventCreateWithFlags(&st->pipe_done[k], cudaEventDisableTiming));
@@ -744,7 +744,7 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
         }
       }
       // poll_every is even, so cur[k] is the same queue at every poll
-      remaining[k] = std::min(remaining[k], hc[k * WF_C_TOTAL + WF_C_EXT0 + cur[k]]);
+      remaining[k] = std::min(remaining[k], hc[k * WF_C_TOTAL + WF_C_EXT(cur[k])]);
       if (remaining[k] == 0) active[k] = false;
       *any = *any || active[k];
     }

@@ -23,37 +23,56 @@
 
 #define WF_NKEY 9     /* material types 0..7 + miss */
 #define WF_KEY_MISS 8
-// counter slots (ints)
-#define WF_C_EXT0 0
-#define WF_C_EXT1 1
-#define WF_C_PROBE 2
-#define WF_C_FETCH 3 /* next unfetched index of the extend queue (persistent extend kernel) */
-#define WF_C_SHADE 4  /* .. WF_C_SHADE + WF_NKEY */
-#define WF_C_TOTAL 16
+// counter slots (ints). Every counter sits on its own 128-byte line: they are all hit by one atomic per warp per
+// kernel, and counters sharing a line would serialise in one L2 slice.
+#define WF_CS 32 /* ints between counters */
+#define WF_C_EXT(cur) ((cur) * WF_CS)            /* the two extend queues */
+#define WF_C_PROBE (2 * WF_CS)
+#define WF_C_FETCH (3 * WF_CS)                   /* next unfetched index of the extend queue (persistent extend kernel) */
+#define WF_C_SHADEK(key) ((4 + (key)) * WF_CS)   /* WF_NKEY shading queues */
+#define WF_C_TOTAL ((4 + WF_NKEY) * WF_CS)
 
 // ctl.z flags
 #define WF_F_MEDIUM 1u  /* cur_volume != 0 */
 #define WF_F_HIT 2u     /* first-hit outputs valid */
 #define WF_F_VOLSCAT 4u /* this bounce is an in-volume scattering event (probe stage uses eval_scattering data) */
 
+// Per-slot path state, interleaved so that what one stage touches for a slot shares 32-byte sectors: slots are
+// visited in queue order (scattered), so every separately allocated 16-byte field costs its own sector.
+//   group A (64 B): ray0, ray1 | hit0, hit1   -- extend reads the first sector and writes the second
+//   group B (64 B): wgt, rad   | bsdf, ctl
+//   group C (32 B): alb, nrm (first-hit outputs)      group D (32 B): med0, med1 (volumes only)
+template <class T, int STRIDE>
+struct WfField {
+  T* p;
+  JT_DEV T& operator[](int s) const { return p[(size_t)STRIDE * (size_t)s]; }
+};
 struct WfBuffers {
-  float4* ray0;  // o.xyz, d.x
-  float4* ray1;  // d.y, d.z, t_hit, -
-  float4* hit0;  // bits(inst), bits(elem), u, v
-  float4* wgt;   // weight.xyz, -
-  float4* rad;   // radiance.xyz, -
-  float4* bsdf;  // f.xyz, pdf_bsdf   (shade -> probe)
-  float4* alb;   // first-hit albedo
-  float4* nrm;   // first-hit normal
-  float4* med0;  // density.xyz, scanisotropy (only when the scene has volumetric materials)
-  float4* med1;  // scattering.xyz
-  uint4* ctl;    // x = sample, y = draw counter, z = bounce | opbounce << 8 | flags << 16, w = max_roughness bits
+  WfField<float4, 4> ray0;  // o.xyz, d.x
+  WfField<float4, 4> ray1;  // d.y, d.z, -, -
+  WfField<float4, 4> hit0;  // bits(inst), bits(elem), u, v
+  WfField<float4, 4> hit1;  // t_hit, -, -, -
+  WfField<float4, 4> wgt;   // weight.xyz, -
+  WfField<float4, 4> rad;   // radiance.xyz, -
+  WfField<float4, 4> bsdf;  // f.xyz, pdf_bsdf   (shade -> probe)
+  WfField<uint4, 4> ctl;    // x = sample, y = draw counter, z = bounce | opbounce << 8 | flags << 16, w = max_roughness bits
+  WfField<float4, 2> alb;   // first-hit albedo
+  WfField<float4, 2> nrm;   // first-hit normal
+  WfField<float4, 2> med0;  // density.xyz, scanisotropy (only when the scene has volumetric materials)
+  WfField<float4, 2> med1;  // scattering.xyz
   int* q_ext[2];
   int* q_shade;  // WF_NKEY segments of n
   int* q_probe;
   int* counts;   // WF_C_TOTAL ints
   int n;         // slots of this pipeline
   int pixel_base;  // slot s renders pixel pixel_base + s (the image may be split over several pipelines)
+  // point the fields at the four interleaved allocations (16 * {4, 4, 2, 2} * n bytes)
+  void bind(float4* a, float4* b, float4* c, float4* d) {
+    ray0.p = a; ray1.p = a + 1; hit0.p = a + 2; hit1.p = a + 3;
+    wgt.p = b; rad.p = b + 1; bsdf.p = b + 2; ctl.p = (uint4*)(b + 3);
+    alb.p = c; nrm.p = c + 1;
+    med0.p = d; med1.p = d + 1;
+  }
 };
 
 JT_DEV unsigned lane_id() { return threadIdx.x & 31u; }
@@ -78,7 +97,7 @@ JT_DEV void wf_append_keyed(int* q_shade, int* counts, int n, int key, int slot)
   if (key >= 0) {
     int leader = __ffs((int)peers) - 1;
     int base = 0;
-    if ((int)lane_id() == leader) base = atomicAdd(counts + WF_C_SHADE + key, __popc(peers));
+    if ((int)lane_id() == leader) base = atomicAdd(counts + WF_C_SHADEK(key), __popc(peers));
     base = __shfl_sync(peers, base, leader);
     q_shade[(size_t)key * n + base + __popc(peers & ((1u << lane_id()) - 1u))] = slot;
   }
@@ -162,7 +181,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(JtDevScene S, WfBuffers B, 
   B.q_ext[0][s] = s;
   if (s == 0) {
     for (int k = 0; k < WF_C_TOTAL; k++) B.counts[k] = 0;
-    B.counts[WF_C_EXT0] = B.n;
+    B.counts[WF_C_EXT(0)] = B.n;
     atomicAdd(counters, (unsigned long long)B.n * (unsigned long long)(sample_end - sample_begin));
   }
 }
@@ -171,7 +190,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(JtDevScene S, WfBuffers B, 
 template <int MODE>
 __global__ void __launch_bounds__(128) k_wf_extend(JtDevScene S, WfBuffers B, int cur, unsigned long long* counters) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  int count = B.counts[WF_C_EXT0 + cur];
+  int count = B.counts[WF_C_EXT(cur)];
   int key = -1, s = -1;
   if (t < count) {
     s = B.q_ext[cur][t];
@@ -180,7 +199,7 @@ __global__ void __launch_bounds__(128) k_wf_extend(JtDevScene S, WfBuffers B, in
     DHit h = intersect_scene<MODE>(S, ray);
     if (h.inst >= 0) {
       B.hit0[s] = make_float4(__int_as_float(h.inst), __int_as_float(h.elem), h.u, h.v);
-      B.ray1[s] = make_float4(r1.x, r1.y, h.t, 0.0f);
+      B.hit1[s] = make_float4(h.t, 0.0f, 0.0f, 0.0f);
       key = S.materials[S.instances[h.inst].material].type;
     } else {
       B.hit0[s] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.0f, 0.0f);
@@ -199,7 +218,7 @@ __global__ void __launch_bounds__(128) k_wf_extend(JtDevScene S, WfBuffers B, in
 __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_extend_persist(JtDevScene S, WfBuffers B, int cur,
                                                                         unsigned long long* counters) {
   const unsigned FULL = 0xFFFFFFFFu;
-  const int count = B.counts[WF_C_EXT0 + cur];
+  const int count = B.counts[WF_C_EXT(cur)];
   const int* queue = B.q_ext[cur];
   uint2 stack[JT_WIDE_STACK];
   PersistLane L;
@@ -210,10 +229,9 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
     __syncwarp();
     int key = -1;
     if (s >= 0 && !live) {  // retire a finished ray: hit record + material-sorted shading queue
-      float4 r1 = B.ray1[s];
       if (L.best.inst >= 0) {
         B.hit0[s] = make_float4(__int_as_float(L.best.inst), __int_as_float(L.best.elem), L.best.u, L.best.v);
-        B.ray1[s] = make_float4(r1.x, r1.y, L.best.t, 0.0f);
+        B.hit1[s] = make_float4(L.best.t, 0.0f, 0.0f, 0.0f);
         key = S.materials[S.instances[L.best.inst].material].type;
       } else {
         B.hit0[s] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.0f, 0.0f);
@@ -261,7 +279,7 @@ JT_DEV bool wf_roulette(f3& weight, WfPath& p, uint64_t key) {
 // One thread per queued slot; queues are laid out key after key, each padded to a warp multiple so a
 // warp only ever sees one material type.
 #ifndef JT_SHADE_MINBLOCKS
-#define JT_SHADE_MINBLOCKS 6 /* tuned on B200: profiles/r01/tuning_variants.txt */
+#define JT_SHADE_MINBLOCKS 5 /* tuned on B200: profiles/r01/tuning_variants.txt */
 #endif
 #ifndef JT_PROBE_MINBLOCKS
 #define JT_PROBE_MINBLOCKS 6
@@ -290,7 +308,7 @@ __global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene
     int off = 0;
 #pragma unroll
     for (int k = 0; k < WF_NKEY; k++) {
-      int c = B.counts[WF_C_SHADE + k];
+      int c = B.counts[WF_C_SHADEK(k)];
       int padded = (c + 31) & ~31;
       if (key < 0 && t >= off && t < off + padded) {
         if (t - off < c) {
@@ -320,7 +338,7 @@ __global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene
     } else {
       float4 h0 = B.hit0[s];
       int inst = __float_as_int(h0.x), elem = __float_as_int(h0.y);
-      float hu = h0.z, hv = h0.w, ht = r1.z;
+      float hu = h0.z, hv = h0.w, ht = B.hit1[s].x;
       bool in_volume = false;
       float distance = ht;
       VolPoint medium;
@@ -488,7 +506,7 @@ __global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene
     }
   }
   wf_append(B.q_probe, B.counts + WF_C_PROBE, to_probe, s);
-  wf_append(B.q_ext[next], B.counts + WF_C_EXT0 + next, to_extend, s);
+  wf_append(B.q_ext[next], B.counts + WF_C_EXT(next), to_extend, s);
   if (SAMPLER == 1 && MODE == MODE_WIDE) {
     unsigned lr = __reduce_add_sync(0xFFFFFFFFu, cnt.light_rays);
     if (lane_id() == 0u && lr) atomicAdd(counters + 2, (unsigned long long)lr);
@@ -523,7 +541,7 @@ __global__ void __launch_bounds__(128, JT_PROBE_MINBLOCKS) k_wf_probe(JtDevScene
       to_extend = wf_finish_sample(S, B, st, P, s, p, f3{rad4.x, rad4.y, rad4.z}, sample_end, counters);
     }
   }
-  wf_append(B.q_ext[next], B.counts + WF_C_EXT0 + next, to_extend, s);
+  wf_append(B.q_ext[next], B.counts + WF_C_EXT(next), to_extend, s);
   unsigned lr = __reduce_add_sync(0xFFFFFFFFu, cnt.light_rays);
   if (lane_id() == 0u && lr) atomicAdd(counters + 2, (unsigned long long)lr);
 }
@@ -531,9 +549,9 @@ __global__ void __launch_bounds__(128, JT_PROBE_MINBLOCKS) k_wf_probe(JtDevScene
 // ---- advance: recycle the consumed queues for the next iteration -------------------------------------------
 __global__ void k_wf_advance(WfBuffers B, int cur) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    B.counts[WF_C_EXT0 + cur] = 0;
+    B.counts[WF_C_EXT(cur)] = 0;
     B.counts[WF_C_PROBE] = 0;
     B.counts[WF_C_FETCH] = 0;
-    for (int k = 0; k < WF_NKEY; k++) B.counts[WF_C_SHADE + k] = 0;
+    for (int k = 0; k < WF_NKEY; k++) B.counts[WF_C_SHADEK(k)] = 0;
   }
 }

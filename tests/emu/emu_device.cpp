@@ -160,14 +160,12 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
   P.accumulate = p->accumulate; P.seed = p->seed;
   DevState st{(float4*)image, (float4*)albedo, (float4*)normal, hits};
   int n = width * height;
-  std::vector<float4> f4[10];
-  for (auto& v : f4) v.assign(n, float4{0, 0, 0, 0});
-  std::vector<uint4> ctl(n);
+  std::vector<float4> ga((size_t)4 * n, float4{0, 0, 0, 0}), gb((size_t)4 * n, float4{0, 0, 0, 0}),
+      gc((size_t)2 * n, float4{0, 0, 0, 0}), gd((size_t)2 * n, float4{0, 0, 0, 0});
   std::vector<int> q0(n), q1(n), qs((size_t)n * WF_NKEY), qp(n), counts(WF_C_TOTAL, 0);
   WfBuffers B;
-  B.ray0 = f4[0].data(); B.ray1 = f4[1].data(); B.hit0 = f4[2].data(); B.wgt = f4[3].data(); B.rad = f4[4].data();
-  B.bsdf = f4[5].data(); B.alb = f4[6].data(); B.nrm = f4[7].data(); B.med0 = f4[8].data(); B.med1 = f4[9].data();
-  B.ctl = ctl.data(); B.q_ext[0] = q0.data(); B.q_ext[1] = q1.data(); B.q_shade = qs.data(); B.q_probe = qp.data();
+  B.bind(ga.data(), gb.data(), gc.data(), gd.data());
+  B.q_ext[0] = q0.data(); B.q_ext[1] = q1.data(); B.q_shade = qs.data(); B.q_probe = qp.data();
   B.counts = counts.data(); B.n = n; B.pixel_base = 0;
   unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   auto run = [&](int threads, auto&& kernel) {
@@ -175,13 +173,13 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
   };
   run(n, [&] { k_wf_generate(e->dev, B, P, begin, end, cnt); });
   int cur = 0, iterations = 0;
-  while (counts[WF_C_EXT0 + cur] > 0) {
+  while (counts[WF_C_EXT(cur)] > 0) {
     int next = cur ^ 1;
-    int ne = counts[WF_C_EXT0 + cur];
+    int ne = counts[WF_C_EXT(cur)];
     if (p->traversal == 1) run(ne, [&] { k_wf_extend<MODE_REF>(e->dev, B, cur, cnt); });
     else run(ne, [&] { k_wf_extend<MODE_WIDE>(e->dev, B, cur, cnt); });
     int ns = 0;
-    for (int k = 0; k < WF_NKEY; k++) ns += (counts[WF_C_SHADE + k] + 31) & ~31;
+    for (int k = 0; k < WF_NKEY; k++) ns += (counts[WF_C_SHADEK(k)] + 31) & ~31;
     if (P.sampler == 1) {
       if (p->traversal == 1) run(ns, [&] { k_wf_shade<1, MODE_REF>(e->dev, B, st, P, next, end, cnt); });
       else run(ns, [&] { k_wf_shade<1, MODE_WIDE>(e->dev, B, st, P, next, end, cnt); });
