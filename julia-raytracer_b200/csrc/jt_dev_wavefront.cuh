@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128) k_wf_extend(JtDevScene S, WfBuffers B, in
 
 // Persistent-warp extend over the wide BVH (jt_dev_persist.cuh): lanes refill from the queue as they finish.
 #ifndef JT_EXTEND_MINBLOCKS
-#define JT_EXTEND_MINBLOCKS 7
+#define JT_EXTEND_MINBLOCKS 6
 #endif
 __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_extend_persist(JtDevScene S, WfBuffers B, int cur,
                                                                         unsigned long long* counters) {
