@@ -63,7 +63,7 @@ struct jt_scene {
   uint64_t launches = 0;
   unsigned persist_blocks = 0;
   // device time of the dominant kernel (extend), measured with CUDA events around every launch
-  cudaEvent_t ext_ev[16] = {};
+  cudaEvent_t ext_ev[64] = {};  // [pipeline][16]: start/stop pairs around the extend launches of the last two batches
   double extend_ms = 0.0;
   uint64_t extend_launches = 0;
   std::vector<jt_state*> states;  // for flushing lazily batched sample ranges
@@ -128,7 +128,7 @@ extern "C" void jt_scene_destroy(jt_scene* sc) {
   for (jt_state* st : sc->states) st->has_pending = false;
   cudaSetDevice(sc->device);
   for (void* p : sc->allocs) cudaFree(p);
-  for (int k = 0; k < 16; k++)
+  for (int k = 0; k < 64; k++)
     if (sc->ext_ev[k]) cudaEventDestroy(sc->ext_ev[k]);
   if (sc->ev_start) cudaEventDestroy(sc->ev_start);
   if (sc->ev_stop) cudaEventDestroy(sc->ev_stop);
@@ -145,7 +145,7 @@ static int scene_create_impl(const jt_scene_desc* d, int device, jt_scene* sc) {
   JT_CUDA(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
   JT_CUDA(cudaEventCreate(&sc->ev_start));
   JT_CUDA(cudaEventCreate(&sc->ev_stop));
-  for (int k = 0; k < 16; k++) JT_CUDA(cudaEventCreate(&sc->ext_ev[k]));
+  for (int k = 0; k < 64; k++) JT_CUDA(cudaEventCreate(&sc->ext_ev[k]));
   memset(&sc->dev, 0, sizeof(sc->dev));
   memset(&sc->stats, 0, sizeof(sc->stats));
 
@@ -665,7 +665,7 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
   if (rc) return rc;
   const int npipe = st->npipe;
   constexpr int poll_every = 4;
-  static_assert(poll_every % 2 == 0 && 4 * poll_every <= 16, "poll_every: even (queue parity at every poll) and within ext_ev");
+  static_assert(poll_every % 2 == 0 && 4 * poll_every <= 16 && 16 * JT_MAX_PIPES <= 64, "poll_every: even (queue parity at every poll) and within ext_ev");
   int cur[JT_MAX_PIPES], remaining[JT_MAX_PIPES];
   bool active[JT_MAX_PIPES];
   // the other pipelines start after everything already enqueued on the main stream
@@ -698,14 +698,14 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
         // appears at most once per iteration)
         unsigned ge = (unsigned)((remaining[k] + 127) / 128), gs = (unsigned)((remaining[k] + 32 * WF_NKEY + 127) / 128);
         const int evi = 2 * (it % (2 * poll_every));
-        if (k == 0) JT_CUDA(cudaEventRecord(sc->ext_ev[evi], q));
+        JT_CUDA(cudaEventRecord(sc->ext_ev[16 * k + evi], q));
         if (MODE == MODE_WIDE) {
           unsigned gp = std::min<unsigned>((unsigned)((remaining[k] + JT_PERSIST_BLOCK - 1) / JT_PERSIST_BLOCK), pgrid);
           k_wf_extend_persist<<<gp, JT_PERSIST_BLOCK, 0, q>>>(sc->dev, B, cur[k], sc->d_counters);
         } else {
           k_wf_extend<MODE><<<ge, 128, 0, q>>>(sc->dev, B, cur[k], sc->d_counters);
         }
-        if (k == 0) JT_CUDA(cudaEventRecord(sc->ext_ev[evi + 1], q));
+        JT_CUDA(cudaEventRecord(sc->ext_ev[16 * k + evi + 1], q));
         if (P.sampler == 1) {
           k_wf_shade<1, MODE><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
           k_wf_probe<MODE><<<ge, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
@@ -734,14 +734,13 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
     for (int k = 0; k < npipe; k++) {
       if (!polled[k]) continue;
       JT_CUDA(cudaEventSynchronize(st->poll_ev[batch & 1][k]));
-      if (k == 0) {
-        // pipeline 0 stands for all of them in the per-kernel timing (same work per pixel on average)
-        for (int sub = 0; sub < poll_every; sub++) {
-          const int evi = 2 * ((batch * poll_every + sub) % (2 * poll_every));
-          float ms = 0.0f;
-          if (cudaEventElapsedTime(&ms, sc->ext_ev[evi], sc->ext_ev[evi + 1]) == cudaSuccess) sc->extend_ms += ms;
-          sc->extend_launches++;
-        }
+      // per-launch duration of every extend launch of every pipeline (the roofline of bench.py divides the bytes of
+      // ALL scene rays by this sum; launches of different pipelines overlap in wall time, each is timed on its stream)
+      for (int sub = 0; sub < poll_every; sub++) {
+        const int evi = 16 * k + 2 * ((batch * poll_every + sub) % (2 * poll_every));
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, sc->ext_ev[evi], sc->ext_ev[evi + 1]) == cudaSuccess) sc->extend_ms += ms;
+        sc->extend_launches++;
       }
       // poll_every is even, so cur[k] is the same queue at every poll
       remaining[k] = std::min(remaining[k], hc[k * WF_C_TOTAL + WF_C_EXT(cur[k])]);
