@@ -61,7 +61,7 @@ struct jt_scene {
   int num_cameras = 0, num_instances = 0;
   unsigned long long* d_counters = nullptr;  // [0] camera paths [1] scene rays [2] light rays
   uint64_t launches = 0;
-  unsigned persist_blocks = 0;
+  unsigned persist_blocks = 0, intersect_blocks = 0;
   // device time of the dominant kernel (extend), measured with CUDA events around every launch
   cudaEvent_t ext_ev[64] = {};  // [pipeline][16]: start/stop pairs around the extend launches of the last two batches
   double extend_ms = 0.0;
@@ -886,7 +886,13 @@ extern "C" int jt_intersect_device(jt_scene* sc, const void* d_rays, int64_t n, 
     if (n > 0x7FFFFFFF) return jt_set_error(JT_ERR_INVALID, "jt_intersect_device: more than 2^31-1 rays per call");
     int* fetch = (int*)(sc->d_counters + 7);
     JT_CUDA(cudaMemsetAsync(fetch, 0, 4, sc->stream));
-    unsigned pblocks = std::min<unsigned>((unsigned)((n + JT_PERSIST_BLOCK - 1) / JT_PERSIST_BLOCK), persist_grid(sc));
+    if (sc->intersect_blocks == 0) {  // one resident wave of THIS kernel (its register count differs from the extend kernel's)
+      int per_sm = 0, sms = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_intersect_persist, JT_PERSIST_BLOCK, 0);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device);
+      sc->intersect_blocks = (unsigned)std::max(1, per_sm) * (unsigned)std::max(1, sms);
+    }
+    unsigned pblocks = std::min<unsigned>((unsigned)((n + JT_PERSIST_BLOCK - 1) / JT_PERSIST_BLOCK), sc->intersect_blocks);
     k_intersect_persist<<<pblocks, JT_PERSIST_BLOCK, 0, sc->stream>>>(sc->dev, (const jt_ray*)d_rays, n, (HitOut*)d_hits, fetch);
   }
   sc->launches++;
