@@ -20,6 +20,8 @@
 // operation order, so t/u/v are bit-identical; the tree only decides WHICH primitives are tested.
 // The closest hit is order independent; exact-t ties are resolved with the per-octant visit
 // ranks computed here from the reference tree (SURVEY.md §8a "tie-break contract").
+#include <omp.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -225,7 +227,7 @@ class Collapser {
     t.reserve_for(recs.size());
     int root = -1;
     // small trees stay on the calling thread: waking the pool costs more than they do
-#pragma omp parallel if (recs.size() > 200000)
+#pragma omp parallel if (recs.size() > 200000) num_threads(build_threads_)
 #pragma omp single nowait
     {
       NodeChunk chunk;
@@ -502,7 +504,7 @@ class Collapser {
     std::vector<Work> jobs(open.begin() + (long)head, open.end());
     std::vector<Sink> sinks(jobs.size());
     const bool big = t.recs.size() > 200000;
-#pragma omp parallel for schedule(dynamic, 1) if (big)
+#pragma omp parallel for schedule(dynamic, 1) if (big) num_threads(build_threads_)
     for (long j = 0; j < (long)jobs.size(); j++) {
       Sink& sk = sinks[(size_t)j];
       sk.nodes.push_back(JtWideNode());
@@ -545,7 +547,7 @@ class Collapser {
       gn += sinks[j].nodes.size() - 1;
       gt += sinks[j].tris.size();
     }
-#pragma omp parallel for schedule(dynamic, 1) if (big)
+#pragma omp parallel for schedule(dynamic, 1) if (big) num_threads(build_threads_)
     for (long j = 0; j < (long)jobs.size(); j++) {
       const Sink& sk = sinks[(size_t)j];
       // descendants: local index c >= 1 lives at node_at + c - 1
@@ -912,7 +914,7 @@ class Collapser {
       const size_t top0 = top.size();
       top.resize(top0 + (size_t)(first - braids[0].first));
       const int64_t base = braids[0].first;
-#pragma omp parallel for schedule(dynamic, 8) if (first - base > 200000)
+#pragma omp parallel for schedule(dynamic, 8) if (first - base > 200000) num_threads(build_threads_)
       for (long j = 0; j < (long)braids.size(); j++) {
         const BraidJob& B = braids[(size_t)j];
         const JtHostInstance& I = insts_[(size_t)B.inst];
@@ -941,6 +943,16 @@ class Collapser {
   const std::vector<JtHostInstance>& insts_;
   JtWideResult* out_;
   std::vector<ShapeRank> shape_ranks_;
+  // Threads of the big builds: JT_BUILD_THREADS, else the OpenMP default -- except under torchrun, which exports
+  // OMP_NUM_THREADS=1 to every rank: there the host cores are split evenly over the local ranks instead.
+  static int default_build_threads() {
+    if (const char* e = getenv("JT_BUILD_THREADS")) return std::max(1, atoi(e));
+    int n = omp_get_max_threads();
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    if (lws && atoi(lws) > 0) n = std::max(n, omp_get_num_procs() / atoi(lws));
+    return std::max(1, n);
+  }
+  int build_threads_ = default_build_threads();
   int braid_max_ = getenv("JT_BRAID_MAX") ? atoi(getenv("JT_BRAID_MAX")) : 1;  // triangles per braided sub-tree; 1 = flatten; 0 = off
   int64_t braid_min_instances_ = getenv("JT_BRAID_MIN_INSTANCES") ? atoll(getenv("JT_BRAID_MIN_INSTANCES")) : 256;
   int64_t flatten_budget_ = (int64_t)48 << 20;  // records (48 B + 32 B of ranks each, plus ~0.2 nodes of 80 B)
