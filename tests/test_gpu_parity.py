@@ -252,3 +252,82 @@ def test_converged_render_matches_the_reference_image(pair, name, sampler, spp, 
     print(f"\n[{name} {sampler} {spp} spp] mean diff {dm:.2f}, RMSE {rmse:.2f} (8-bit units)")
     st.close() if hasattr(st, "close") else None
     assert dm < mean_tol and rmse < rmse_tol, (dm, rmse)
+
+
+def test_baseline_config_c1_full_size_is_bit_exact(pair):
+    """BASELINE config C1 at its full size -- cornellbox, naive sampler, 720 px, 16 spp (8.3 M camera paths): the GPU's
+    reference-order mode equals the oracle bit for bit, the fast mode to <= 2e-3 of the pixels (residual class)."""
+    o, d = pair("cornellbox")
+    op = orc.make_params(resolution=720, samples=16, batch=16, sampler=2, seed=0)
+    w, h = o.make_state(op)
+    assert (w, h) == (720, 720)
+    o.trace_samples(op)
+    ref = o.get_state()
+    for traversal in ("reference", "wide"):
+        p = _params(scene="cornellbox", resolution=720, samples=16, batch=1, sampler=2, gpu_traversal=traversal)
+        st = trace.make_trace_state(d, p)
+        for _ in range(16):  # the reference's own call pattern: samples / batch calls (src/jtrace.jl:83-94)
+            trace.trace_samples(st, d, None, None, p)
+        st.sync()
+        img = st.image.reshape(h, w, 4)
+        if traversal == "reference":
+            assert np.array_equal(img, ref["image"]) and np.array_equal(st.hits.reshape(h, w), ref["hits"])
+            assert np.array_equal(st.albedo.reshape(h, w, 3), ref["albedo"])
+            assert np.array_equal(st.normal.reshape(h, w, 3), ref["normal"])
+        else:
+            assert (np.abs(img - ref["image"]).max(axis=-1) > 1e-4).mean() <= 2e-3
+        st.close()
+
+
+# BASELINE configs C2-C5 at their full image sizes; spp reduced (the properties below do not depend on it)
+FULL_SIZE = [("features1", 1280, (1280, 533)), ("materials1", 1280, (1280, 533)), ("classroom", 1280, (1280, 720)),
+             ("ecosys", 1920, (1920, 960))]
+
+
+@pytest.mark.parametrize("name,res,size", FULL_SIZE)
+def test_baseline_configs_full_size_properties(pair, name, res, size):
+    """Size-independent properties at the BASELINE image sizes (path sampler):
+    * the fast traversal (wide / flattened BVH, wavefront) differs from the reference-order traversal on at most
+      2e-3 of the pixels (residual class) and both count the same camera paths;
+    * determinism: the same sample range rendered twice is bit-identical;
+    * sharding: two disjoint sample ranges rendered as separate sum-mode states add up to the one-state render;
+    * alpha / hits bookkeeping: hits <= spp and alpha == hits / spp in running-mean mode."""
+    _, d = pair(name)
+    spp = 4
+    p = _params(scene=name, resolution=res, samples=spp, batch=spp, sampler=1)
+    imgs = {}
+    for traversal in ("wide", "reference"):
+        q = _params(scene=name, resolution=res, samples=spp, batch=spp, sampler=1, gpu_traversal=traversal)
+        st = trace.make_trace_state(d, q)
+        assert (st.width, st.height) == size
+        d.counters(reset=True)
+        trace.trace_samples(st, d, None, None, q)
+        st.sync()
+        assert d.counters()["camera_paths"] == size[0] * size[1] * spp
+        imgs[traversal] = (st.image.copy(), st.hits.copy())
+        st.close()
+    img, hits = imgs["wide"]
+    assert np.isfinite(img).all()
+    differing = np.abs(img - imgs["reference"][0]).max(axis=-1) > 1e-4
+    assert differing.mean() <= 2e-3, differing.mean()
+    assert hits.max() <= spp and np.allclose(img[:, 3], hits / np.float32(spp), atol=1e-6)
+    again = trace.make_trace_state(d, p)
+    trace.trace_sample_range(again, d, p, 0, 1)  # different chunking, same samples
+    trace.trace_sample_range(again, d, p, 1, spp)
+    again.sync()
+    assert np.array_equal(again.image, img) and np.array_equal(again.hits, hits)
+    again.close()
+    whole = trace.make_trace_state(d, p, accumulate=1)
+    trace.trace_sample_range(whole, d, p, 0, spp)
+    whole.set_samples(1)
+    whole.sync()
+    parts = []
+    for g in range(2):
+        s = trace.make_trace_state(d, p, accumulate=1)
+        trace.trace_sample_range(s, d, p, g * spp // 2, (g + 1) * spp // 2)
+        s.set_samples(1)
+        s.sync()
+        parts.append(s.image.copy())
+        s.close()
+    assert np.allclose(parts[0] + parts[1], whole.image, rtol=1e-6, atol=1e-6)
+    whole.close()
