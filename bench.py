@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--scene", default="classroom")
     ap.add_argument("--sampler", default="path", choices=["path", "naive"])
     ap.add_argument("--resolution", type=int, default=1280)
-    ap.add_argument("--spp-per-step", type=int, default=128)
+    ap.add_argument("--spp-per-step", type=int, default=512)
     ap.add_argument("--traversal", default="wide", choices=["wide", "reference"])
     ap.add_argument("--integrator", default="wavefront", choices=["wavefront", "megakernel"])
     ap.add_argument("--cpu-spp", type=int, default=2, help="samples per pixel of the bounded CPU-baseline sample")

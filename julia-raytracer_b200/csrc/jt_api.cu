@@ -97,7 +97,7 @@ struct jt_state {
   jt_params pending_params;
 };
 
-#define JT_LAZY_SPP 128 /* each flushed chunk ends in a drain phase (shrinking queues): 8 spp 305, 32 spp 322, 128 spp 333 Msamples/s */
+#define JT_LAZY_SPP 512 /* each flushed chunk ends in a drain phase (shrinking queues): 8 / 32 / 128 / 512 / 2048 spp per chunk: 305 / 322 / 333 (v3), 383 / 391 / 393 (v4) Msamples/s */
 #ifndef JT_DEFAULT_PIPES
 #define JT_DEFAULT_PIPES 2 /* measured on B200: 338 -> 357 Msamples/s (classroom), profiles/r01/tuning_variants.txt */
 #endif

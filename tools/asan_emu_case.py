@@ -25,3 +25,17 @@ for s in ['synthetic_all','synthetic_one','cornellbox','features1','classroom','
             p=orc.make_params(resolution=32, samples=2, batch=2, sampler=sampler, traversal=trav)
             e.trace(p,32,max(1,int(32/ float(sc.cameras[0].aspect))),0,2,wavefront=True); e.trace(p,32,max(1,int(32/float(sc.cameras[0].aspect))),0,2,wavefront=False)
     print('asan ok', s, flush=True)
+# braided / flattened instance paths on small scenes (entry records at BLAS sub-trees, instance-space leaf tests)
+for braid in ('1', '16'):
+    os.environ['JT_BRAID_MAX'] = braid
+    os.environ['JT_BRAID_MIN_INSTANCES'] = '1'
+    for s in ['features1', 'classroom', 'synthetic_all']:
+        sc = synth.make_scene(s) if s.startswith('synth') else orc.jt.load_scene(os.path.join(ROOT, 'assets', 'scenes', f'{s}.jtscene'))
+        b=bvhm.make_scene_bvh(sc); Lt=lm.make_trace_lights(sc)
+        o=orc.Oracle(sc,b,Lt); e=emu.Emu(sc,b,Lt)
+        p=orc.make_params(resolution=48, samples=2, batch=2, sampler=1); w,h=o.make_state(p)
+        rays=raygen.camera_rays(o,p,w,h,3000,seed=3); sec=raygen.secondary_rays(rays,o.intersect(rays),seed=4)
+        for trav in (0,3): e.intersect(np.concatenate([rays,sec]),trav)
+        p=orc.make_params(resolution=32, samples=2, batch=2, sampler=1, traversal=0)
+        e.trace(p,32,max(1,int(32/float(sc.cameras[0].aspect))),0,2,wavefront=True)
+        print('asan ok', s, 'braid', braid, e.stats()['flattened'], flush=True)
