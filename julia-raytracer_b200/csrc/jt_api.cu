@@ -640,10 +640,12 @@ static int wf_prepare(jt_scene* sc, jt_state* st) {
     if ((rc = alloc((void**)&ga, n * 64)) || (rc = alloc((void**)&gb, n * 64)) || (rc = alloc((void**)&gc, n * 32)) ||
         (rc = alloc((void**)&gd, n * 32)) ||
         (rc = alloc((void**)&B.q_ext[0], n * 4)) || (rc = alloc((void**)&B.q_ext[1], n * 4)) ||
+        (rc = alloc((void**)&B.regen, ((n + 15) & ~(size_t)15) + 16)) ||
         (rc = alloc((void**)&B.q_shade, n * 4 * WF_NKEY)) || (rc = alloc((void**)&B.q_probe, n * 4)) ||
         (rc = alloc((void**)&B.counts, WF_C_TOTAL * 4)))
       return rc;
     B.bind(ga, gb, gc, gd);
+    JT_CUDA(cudaMemset(B.regen, 0, ((n + 15) & ~(size_t)15) + 16));
     st->pipe_stream[k] = sc->stream;
     if (k > 0) JT_CUDA(cudaStreamCreateWithFlags(&st->pipe_stream[k], cudaStreamNonBlocking));
     JT_CUDA(cudaEventCreateWithFlags(&st->pipe_done[k], cudaEventDisableTiming));
@@ -714,7 +716,7 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
           k_wf_shade<2, MODE><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
           sc->launches += 3;
         }
-        k_wf_advance<<<1, 32, 0, q>>>(B, cur[k]);
+        k_wf_regen<<<(unsigned)((B.n + WF_REGEN_BLOCK * WF_REGEN_PER_THREAD - 1) / (WF_REGEN_BLOCK * WF_REGEN_PER_THREAD)), WF_REGEN_BLOCK, 0, q>>>(B, cur[k]);
         cur[k] = next;
       }
       st->wf_iterations++;

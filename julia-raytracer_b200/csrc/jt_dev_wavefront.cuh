@@ -61,6 +61,7 @@ struct WfBuffers {
   WfField<float4, 2> med0;  // density.xyz, scanisotropy (only when the scene has volumetric materials)
   WfField<float4, 2> med1;  // scattering.xyz
   int* q_ext[2];
+  unsigned char* regen;  // per slot: 1 = a new camera ray was started in place this iteration (k_wf_regen queues it)
   int* q_shade;  // WF_NKEY segments of n
   int* q_probe;
   int* counts;   // WF_C_TOTAL ints
@@ -502,7 +503,7 @@ __global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene
       wf_store_ctl(B, s, p);
     } else {
       to_probe = false;
-      to_extend = wf_finish_sample(S, B, st, P, s, p, radiance, sample_end, counters);
+      if (wf_finish_sample(S, B, st, P, s, p, radiance, sample_end, counters)) B.regen[s] = 1;  // queued in pixel order by k_wf_regen
     }
   }
   wf_append(B.q_probe, B.counts + WF_C_PROBE, to_probe, s);
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(128, JT_PROBE_MINBLOCKS) k_wf_probe(JtDevScene
       to_extend = true;
     } else {
       float4 rad4 = B.rad[s];
-      to_extend = wf_finish_sample(S, B, st, P, s, p, f3{rad4.x, rad4.y, rad4.z}, sample_end, counters);
+      if (wf_finish_sample(S, B, st, P, s, p, f3{rad4.x, rad4.y, rad4.z}, sample_end, counters)) B.regen[s] = 1;
     }
   }
   wf_append(B.q_ext[next], B.counts + WF_C_EXT(next), to_extend, s);
@@ -546,12 +547,67 @@ __global__ void __launch_bounds__(128, JT_PROBE_MINBLOCKS) k_wf_probe(JtDevScene
   if (lane_id() == 0u && lr) atomicAdd(counters + 2, (unsigned long long)lr);
 }
 
-// ---- advance: recycle the consumed queues for the next iteration -------------------------------------------
-__global__ void k_wf_advance(WfBuffers B, int cur) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+// ---- regen + advance -------------------------------------------------------------------------------------------
+// Closes an iteration: (1) the slots that started a new camera ray this iteration (flagged by shade / probe) are
+// appended to the next extend queue IN SLOT (= PIXEL) ORDER, chunk by chunk, so that camera rays of neighbouring
+// pixels sit in neighbouring lanes of the extend kernel -- queues built by atomics scatter them among the bounce rays,
+// and the same mix traverses 11 % slower (tools/exp_coherence.py: 2 534 vs 2 827 Mrays/s on classroom);
+// (2) the consumed queues' counters are recycled.
+#define WF_REGEN_BLOCK 256
+#define WF_REGEN_PER_THREAD 16 /* one 128-bit load of flags */
+#ifndef JT_EMU_COUNT
+__global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(WfBuffers B, int cur) {
+  __shared__ int warp_sums[WF_REGEN_BLOCK / 32];
+  __shared__ int block_base;
+  const int next = cur ^ 1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     B.counts[WF_C_EXT(cur)] = 0;
     B.counts[WF_C_PROBE] = 0;
     B.counts[WF_C_FETCH] = 0;
     for (int k = 0; k < WF_NKEY; k++) B.counts[WF_C_SHADEK(k)] = 0;
   }
+  const int first = (blockIdx.x * WF_REGEN_BLOCK + threadIdx.x) * WF_REGEN_PER_THREAD;
+  unsigned flags = 0u;  // bit i: slot first + i regenerated
+  if (first + WF_REGEN_PER_THREAD <= B.n) {
+    uint4 v = *reinterpret_cast<const uint4*>(B.regen + first);
+    unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+      for (int j = 0; j < 4; j++) flags |= ((w[k] >> (8 * j)) & 1u) << (4 * k + j);
+    if (flags) *reinterpret_cast<uint4*>(B.regen + first) = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    for (int i = 0; i < WF_REGEN_PER_THREAD && first + i < B.n; i++)
+      if (B.regen[first + i]) {
+        flags |= 1u << i;
+        B.regen[first + i] = 0;
+      }
+  }
+  const int mine = __popc(flags);
+  // block-wide exclusive scan of `mine`
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+    if ((int)lane_id() >= d) incl += t;
+  }
+  const int warp = threadIdx.x >> 5;
+  if (lane_id() == 31u) warp_sums[warp] = incl;
+  __syncthreads();
+  int warp_off = 0, total = 0;
+#pragma unroll
+  for (int k = 0; k < WF_REGEN_BLOCK / 32; k++) {
+    int v = warp_sums[k];
+    if (k < warp) warp_off += v;
+    total += v;
+  }
+  if (threadIdx.x == 0) block_base = total ? atomicAdd(B.counts + WF_C_EXT(next), total) : 0;
+  __syncthreads();
+  int at = block_base + warp_off + incl - mine;
+  while (flags) {
+    int i = __ffs((int)flags) - 1;
+    flags &= flags - 1u;
+    B.q_ext[next][at++] = first + i;
+  }
 }
+#endif

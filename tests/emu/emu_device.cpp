@@ -166,6 +166,9 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
   WfBuffers B;
   B.bind(ga.data(), gb.data(), gc.data(), gd.data());
   B.q_ext[0] = q0.data(); B.q_ext[1] = q1.data(); B.q_shade = qs.data(); B.q_probe = qp.data();
+  std::vector<unsigned char> regen((size_t)n + 32, 0);
+  B.regen = regen.data();
+  auto q_next_append = [](WfBuffers& Bq, int nx, int sl) { Bq.q_ext[nx][Bq.counts[WF_C_EXT(nx)]++] = sl; };
   B.counts = counts.data(); B.n = n; B.pixel_base = 0;
   unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   auto run = [&](int threads, auto&& kernel) {
@@ -191,8 +194,14 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
     } else {
       run(ns, [&] { k_wf_shade<2, MODE_REF>(e->dev, B, st, P, next, end, cnt); });
     }
-    emu_blockIdx.x = 0;
-    k_wf_advance(B, cur);
+    // k_wf_regen, sequentially: regenerated slots join the next extend queue in slot order; counters recycled
+    for (int sl = 0; sl < n; sl++)
+      if (regen[sl]) {
+        regen[sl] = 0;
+        q_next_append(B, next, sl);
+      }
+    counts[WF_C_EXT(cur)] = 0; counts[WF_C_PROBE] = 0; counts[WF_C_FETCH] = 0;
+    for (int k = 0; k < WF_NKEY; k++) counts[WF_C_SHADEK(k)] = 0;
     cur = next;
     iterations++;
   }
