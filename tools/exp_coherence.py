@@ -52,6 +52,11 @@ cases = {
     # every ray (camera and bounce) ordered by the pixel it belongs to: what a queue compacted in slot order looks like
     "all_in_pixel_order": np.concatenate([prim, sec])[np.argsort(np.concatenate([np.arange(n), secpix]), kind="stable")],
     "camera_pixel_order_then_bounce_pixel_order": np.concatenate([prim, sec[np.argsort(secpix, kind="stable")]]),
+    # bounce rays bucketed by direction octant (what an 8-way keyed append in shade / probe would give)
+    "camera_pixel_order_then_bounce_by_octant": np.concatenate([prim, sec[np.argsort(
+        (sec["d"][:, 0] < 0) * 1 + (sec["d"][:, 1] < 0) * 2 + (sec["d"][:, 2] < 0) * 4, kind="stable")]]),
+    "camera_pixel_order_then_bounce_by_octant_and_pixel": np.concatenate([prim, sec[np.lexsort(
+        (secpix, (sec["d"][:, 0] < 0) * 1 + (sec["d"][:, 1] < 0) * 2 + (sec["d"][:, 2] < 0) * 4))]]),
 }
 out = {"scene": name, "camera": n, "bounce": nsec}
 for label, rays in cases.items():
