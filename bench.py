@@ -68,18 +68,21 @@ def workload_name(args, w, h):
 # ------------------------------------------------------------------------------------------------
 def cpu_run(args, scene, sbvh, lts, spp, steps=1, warmup=0):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    # all host threads: torchrun exports OMP_NUM_THREADS=1 to every rank, which would cripple the CPU arm (libgomp
+    # reads the variable when the oracle library is loaded, i.e. at the import below)
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     import orc  # the ONLY place bench.py touches oracle/: cpu_baseline and --impl reference
     o = orc.Oracle(scene, sbvh, lts)
     p = orc.make_params(resolution=args.resolution, samples=1 << 30, batch=spp,
                         sampler=1 if args.sampler == "path" else 2)
     w, h = o.make_state(p)
-    cores = os.cpu_count() or 1
+    cores = os.cpu_count() or 1  # passed explicitly: independent of OMP_NUM_THREADS and of who loaded libgomp first
     for _ in range(warmup):
-        o.trace_samples(p)
+        o.trace_samples(p, threads=cores)
     o.counters(reset=True)
     t0 = time.perf_counter()
     for _ in range(steps):
-        o.trace_samples(p)
+        o.trace_samples(p, threads=cores)
     dt = time.perf_counter() - t0
     c = o.counters()
     return dict(seconds=dt, paths=c["camera_paths"], counters=c, cores=cores, width=w, height=h,
