@@ -16,6 +16,7 @@
 #include "jt_internal.h"
 #include "jt_rng.h"
 
+#undef JT_DEV
 #define JT_DEV __device__ __forceinline__
 
 struct f3 {
