@@ -698,7 +698,9 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
         const int next = cur[k] ^ 1;
         // grids sized from the last polled queue length (an upper bound: queues only shrink, because every slot
         // appears at most once per iteration)
-        unsigned ge = (unsigned)((remaining[k] + 127) / 128), gs = (unsigned)((remaining[k] + 32 * WF_NKEY + 127) / 128);
+        unsigned ge = (unsigned)((remaining[k] + 127) / 128);
+        unsigned gs = (unsigned)((remaining[k] + 32 * WF_NKEY + JT_SHADE_BLOCK - 1) / JT_SHADE_BLOCK);
+        unsigned gpr = (unsigned)((remaining[k] + JT_PROBE_BLOCK - 1) / JT_PROBE_BLOCK);
         const int evi = 2 * (it % (2 * poll_every));
         JT_CUDA(cudaEventRecord(sc->ext_ev[16 * k + evi], q));
         if (MODE == MODE_WIDE) {
@@ -709,11 +711,11 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
         }
         JT_CUDA(cudaEventRecord(sc->ext_ev[16 * k + evi + 1], q));
         if (P.sampler == 1) {
-          k_wf_shade<1, MODE><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
-          k_wf_probe<MODE><<<ge, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+          k_wf_shade<1, MODE><<<gs, JT_SHADE_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+          k_wf_probe<MODE><<<gpr, JT_PROBE_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
           sc->launches += 4;
         } else {
-          k_wf_shade<2, MODE><<<gs, 128, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
+          k_wf_shade<2, MODE><<<gs, JT_SHADE_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
           sc->launches += 3;
         }
         k_wf_regen<<<(unsigned)((B.n + WF_REGEN_BLOCK * WF_REGEN_PER_THREAD - 1) / (WF_REGEN_BLOCK * WF_REGEN_PER_THREAD)), WF_REGEN_BLOCK, 0, q>>>(B, cur[k]);

@@ -17,7 +17,9 @@
 #ifndef JT_FETCH_THRESHOLD
 #define JT_FETCH_THRESHOLD 20
 #endif
-#define JT_PERSIST_BLOCK 128
+#ifndef JT_PERSIST_BLOCK
+#define JT_PERSIST_BLOCK 384 /* x 2 blocks per SM; 128 x 6: -5 %, 256 x 3: -1 %, 768 x 1: -1 % (tuning_variants.txt) */
+#endif
 
 struct PersistLane {
   WideRay R;            // current space (world or instance)

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(128) k_wf_extend(JtDevScene S, WfBuffers B, in
 
 // Persistent-warp extend over the wide BVH (jt_dev_persist.cuh): lanes refill from the queue as they finish.
 #ifndef JT_EXTEND_MINBLOCKS
-#define JT_EXTEND_MINBLOCKS 6
+#define JT_EXTEND_MINBLOCKS 2
 #endif
 __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_extend_persist(JtDevScene S, WfBuffers B, int cur,
                                                                         unsigned long long* counters) {
@@ -279,6 +279,12 @@ JT_DEV bool wf_roulette(f3& weight, WfPath& p, uint64_t key) {
 // ---- shade ---------------------------------------------------------------------------------------------
 // One thread per queued slot; queues are laid out key after key, each padded to a warp multiple so a
 // warp only ever sees one material type.
+#ifndef JT_SHADE_BLOCK
+#define JT_SHADE_BLOCK 128
+#endif
+#ifndef JT_PROBE_BLOCK
+#define JT_PROBE_BLOCK 128
+#endif
 #ifndef JT_SHADE_MINBLOCKS
 #define JT_SHADE_MINBLOCKS 5 /* tuned on B200: profiles/r01/tuning_variants.txt */
 #endif
@@ -300,7 +306,7 @@ JT_DEV bool wf_inline_mis(const JtDevScene& S, f3 position, f3 incoming, f3 f, f
 }
 
 template <int SAMPLER, int MODE>
-__global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
+__global__ void __launch_bounds__(JT_SHADE_BLOCK, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
                                                   int sample_end, unsigned long long* counters) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int key = -1, s = -1;
@@ -516,7 +522,7 @@ __global__ void __launch_bounds__(128, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene
 
 // ---- probe ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(128, JT_PROBE_MINBLOCKS) k_wf_probe(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
+__global__ void __launch_bounds__(JT_PROBE_BLOCK, JT_PROBE_MINBLOCKS) k_wf_probe(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
                                                   int sample_end, unsigned long long* counters) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int count = B.counts[WF_C_PROBE];
