@@ -231,7 +231,7 @@ class Collapser {
     small_sweep_ = recs.size() > ((size_t)2 << 20);
     int root = -1;
     // small trees stay on the calling thread: waking the pool costs more than they do
-#pragma omp parallel if (recs.size() > 200000) num_threads(build_threads_)
+#pragma omp parallel if ((int64_t)recs.size() > parallel_min_) num_threads(build_threads_)
 #pragma omp single nowait
     {
       NodeChunk chunk;
@@ -507,7 +507,7 @@ class Collapser {
     }
     std::vector<Work> jobs(open.begin() + (long)head, open.end());
     std::vector<Sink> sinks(jobs.size());
-    const bool big = t.recs.size() > 200000;
+    const bool big = (int64_t)t.recs.size() > parallel_min_;
 #pragma omp parallel for schedule(dynamic, 1) if (big) num_threads(build_threads_)
     for (long j = 0; j < (long)jobs.size(); j++) {
       Sink& sk = sinks[(size_t)j];
@@ -918,7 +918,7 @@ class Collapser {
       const size_t top0 = top.size();
       top.resize(top0 + (size_t)(first - braids[0].first));
       const int64_t base = braids[0].first;
-#pragma omp parallel for schedule(dynamic, 8) if (first - base > 200000) num_threads(build_threads_)
+#pragma omp parallel for schedule(dynamic, 8) if (first - base > parallel_min_) num_threads(build_threads_)
       for (long j = 0; j < (long)braids.size(); j++) {
         const BraidJob& B = braids[(size_t)j];
         const JtHostInstance& I = insts_[(size_t)B.inst];
@@ -957,6 +957,8 @@ class Collapser {
     return std::max(1, n);
   }
   int build_threads_ = default_build_threads();
+  // trees below this many records are built on the calling thread (JT_BUILD_PARALLEL_MIN: lowered by the tests)
+  int64_t parallel_min_ = getenv("JT_BUILD_PARALLEL_MIN") ? atoll(getenv("JT_BUILD_PARALLEL_MIN")) : 200000;
   bool small_sweep_ = false;
   int braid_max_ = getenv("JT_BRAID_MAX") ? atoi(getenv("JT_BRAID_MAX")) : 1;  // triangles per braided sub-tree; 1 = flatten; 0 = off
   int64_t braid_min_instances_ = getenv("JT_BRAID_MIN_INSTANCES") ? atoll(getenv("JT_BRAID_MIN_INSTANCES")) : 256;
