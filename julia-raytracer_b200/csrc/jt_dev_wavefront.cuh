@@ -10,13 +10,17 @@
 //              key = material type of the hit instance, or MISS: material-sorted shading queues
 //   shade    : miss -> environment; volume distance sampling; eval position / normal / material;
 //              opacity pass-through; emission; BSDF-or-light direction sampling; delta lobes and the
-//              naive sampler finish their bounce here                            -> q_probe | q_extend
+//              naive sampler finish their bounce here; so do (wide mode) the MIS bounces whose ray
+//              cannot reach any area light, for which sample_lights_pdf needs no BLAS walk
+//                                                                       -> q_probe | q_extend | regen flag
 //   probe    : sample_lights_pdf (the chained intersect_instance_bvh probes), MIS weight,
-//              Russian roulette                                                           -> q_extend
+//              Russian roulette                                                   -> q_extend | regen flag
+//   regen    : slots flagged as "new camera ray started in place" join the next extend queue in
+//              slot (= pixel) order; consumed queue counters are recycled
 // A slot that terminates a sample accumulates it (running mean or sum) and regenerates the next
 // sample of ITS pixel in place, so samples of one pixel are still accumulated in order (Q13) with
 // no atomics on the image. Queue appends are warp-aggregated: one atomicAdd per warp per queue,
-// lane offsets from ballot / match_any masks.
+// lane offsets from ballot / match_any masks; the per-slot state is interleaved (WfBuffers).
 #pragma once
 #include "jt_dev_persist.cuh"
 #include "jt_dev_trace.cuh"
