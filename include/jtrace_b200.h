@@ -182,7 +182,8 @@ JT_API int jt_scene_counters(jt_scene* scene, jt_counters* out, int reset);
 typedef struct {
   int64_t wide_nodes, wide_node_bytes, prim_records, prim_record_bytes;
   int64_t inlined_instances, instanced_instances, texture_bytes, total_device_bytes;
-  int64_t _reserved[8];
+  int64_t _reserved[8]; /* [0] depth of the top-level wide BVH, [1] deepest BLAS, [2] instances opened into the
+                           top-level tree (flattened / braided; see INTEGRATION.md "Environment knobs") */
 } jt_scene_stats;
 JT_API int jt_scene_get_stats(jt_scene* scene, jt_scene_stats* out);
 
