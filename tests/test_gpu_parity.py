@@ -225,7 +225,7 @@ def test_main_drop_in(tmp_path):
 # (scene, sampler, spp, max |mean difference|, max RMSE) in 8-bit sRGB units after the same box reduction to 160 px the goldens got.
 # The goldens are the reference's OWN shipped renders (1280 px, unknown spp, unseeded RNG, full asset set): classroom
 # misses texture3.png here (white instead), hence its looser bound.
-# Measured on a B200 (profiles/r01/pytest_gpu_*.log): mean diff 0.02 / 0.00 / 0.12 / 0.00 / 0.30 / 0.57, RMSE 0.79 / 0.60 /
+# Measured on a B200 (profiles/r01/pytest_gpu_*.log): mean diff 0.09 / 0.00 / 0.12 / 0.00 / 0.30 / 0.57, RMSE 0.84 / 0.60 /
 # 1.26 / 0.83 / 1.77 / 2.49 -- the bounds are about twice that.
 CONVERGED_CASES = [("cornellbox", "path", 1024, 0.5, 2.0), ("materials1", "path", 512, 0.5, 1.5),
                    ("materials1", "naive", 1024, 0.8, 3.0), ("features1", "path", 512, 0.5, 2.0),
