@@ -33,7 +33,7 @@ typedef enum {
   JT_ERR_CUDA = -2,        /* a CUDA runtime call failed */
   JT_ERR_NO_DEVICE = -3,   /* no CUDA device: there is no CPU fallback */
   JT_ERR_UNSUPPORTED = -4, /* feature that also crashes the reference */
-  JT_ERR_NCCL = -5,
+  JT_ERR_PEER = -5,        /* multi-GPU group: a member device failed (message names the member) */
   JT_ERR_INTERNAL = -6
 } jt_status;
 
@@ -133,7 +133,7 @@ typedef struct {
   int32_t camera;       /* 1-based index after find_camera (src/jtrace.jl:61) */
   int32_t resolution;
   int32_t samples;
-  int32_t bounces;
+  int32_t bounces;      /* 0..254 with the wavefront integrator (JT_ERR_INVALID otherwise) */
   int32_t sampler;      /* 1 = path, 2 = naive (src/cli.jl:88, :111-116) */
   int32_t clamp;        /* Params.clamp::Int (src/cli.jl:105) */
   int32_t nocaustics;
@@ -161,8 +161,10 @@ typedef struct {
   uint64_t scene_rays;        /* intersect_scene_bvh calls   (src/trace.jl:298,490) */
   uint64_t light_rays;        /* intersect_instance_bvh calls (src/trace.jl:1025) */
   uint64_t kernel_launches;   /* CUDA kernels launched by the library */
-  uint64_t _reserved[4];      /* [0] microseconds spent in the extend (closest-hit) kernel, CUDA events
-                                 [1] number of extend launches                                         */
+  uint64_t extend_kernel_us;  /* device time of the dominant kernel (extend = closest hit), summed over its launches,
+                                 CUDA events on the launching streams */
+  uint64_t extend_launches;   /* number of extend launches timed */
+  uint64_t _reserved[2];
 } jt_counters;
 
 typedef struct jt_scene jt_scene; /* device-resident scene: SceneData + SceneBvh + TraceLights */
@@ -182,8 +184,10 @@ JT_API int jt_scene_counters(jt_scene* scene, jt_counters* out, int reset);
 typedef struct {
   int64_t wide_nodes, wide_node_bytes, prim_records, prim_record_bytes;
   int64_t inlined_instances, instanced_instances, texture_bytes, total_device_bytes;
-  int64_t _reserved[8]; /* [0] depth of the top-level wide BVH, [1] deepest BLAS, [2] instances opened into the
-                           top-level tree (flattened / braided; see INTEGRATION.md "Environment knobs") */
+  int64_t wide_depth_top;      /* depth of the top-level wide BVH */
+  int64_t wide_depth_blas;     /* deepest instanced BLAS */
+  int64_t opened_instances;    /* instances opened into the top-level tree (flattened / braided; INTEGRATION.md knobs) */
+  int64_t _reserved[5];
 } jt_scene_stats;
 JT_API int jt_scene_get_stats(jt_scene* scene, jt_scene_stats* out);
 
@@ -202,7 +206,11 @@ JT_API int jt_state_download(jt_state* state, float* image_rgba, float* albedo_r
 JT_API int jt_state_download_srgb8(jt_state* state, uint8_t* rgba8);
 /* Raw device pointers of the accumulators (float4 image, float4-padded albedo / normal, int32
  * hits) so that a host that owns a communicator (torch.distributed / NCCL) can reduce them in
- * place across GPUs. `count` = width*height. */
+ * place across GPUs. `count` = width*height.
+ * Ordering: the call flushes the lazily batched samples and BLOCKS until every kernel the library enqueued for this
+ * state has completed, so the caller may reduce on any stream right away. The caller must in turn synchronise ITS
+ * stream before the next library call on this state (jt_state_set_samples + jt_state_download read the buffers on
+ * the library's own non-blocking stream). */
 JT_API int jt_state_device_buffers(jt_state* state, void** image, void** albedo, void** normal,
                                    void** hits, int64_t* count);
 /* After an external sum-reduction across ranks: set the number of samples the buffers hold. */
@@ -211,8 +219,8 @@ JT_API int jt_state_set_samples(jt_state* state, int32_t samples);
 /* ---- the hot path --------------------------------------------------------------------------- */
 /* trace_samples (src/trace.jl:215-274): advances state.samples by params.batch (clamped to
  * params.samples). Lazily batched: the reference calls this samples/batch times with batch = 1 by default,
- * so contiguous requests are merged and launched in chunks (32 samples) or at the next synchronisation
- * point (download, jt_synchronize, counters, device_buffers). Nothing is copied back. */
+ * so contiguous requests are merged and launched in chunks of 512 samples (JT_LAZY_SPP) or at the next
+ * synchronisation point (download, jt_synchronize, counters, device_buffers). Nothing is copied back. */
 JT_API int jt_trace_samples(jt_scene* scene, jt_state* state, const jt_params* params);
 /* Same loop body for an explicit range of global sample indices [begin, end): the unit that
  * is sharded across GPUs. Does not touch state.samples bookkeeping beyond adding end-begin. */
@@ -238,6 +246,54 @@ JT_API int jt_sample_camera(jt_scene* scene, const jt_params* params, int32_t wi
 /* Device-resident variant used by the benchmark: rays and hits are device pointers. */
 JT_API int jt_intersect_device(jt_scene* scene, const void* d_rays, int64_t n, int traversal,
                                void* d_hits);
+
+/* ---- multi-GPU group: ONE host thread drives N devices --------------------------------------
+ * The reference's call site (src/jtrace.jl:83-94) is single-threaded, so sharding lives inside the library: the scene
+ * is staged once and replicated on every member device, each member has a worker thread with its own streams, a
+ * requested range of global sample indices is split into contiguous sub-ranges (one per member; RNG streams are keyed
+ * by the global sample index, so the union is exactly the single-GPU sample set), members accumulate plain SUMS, and
+ * the download runs ONE fused kernel on member 0 that reads every member's four sum buffers over NVLink peer access
+ * (P2P loads; 52 B per pixel per remote member), adds them in member order, divides by the sample count and packs the
+ * reference's host layouts. No NCCL is involved: 8 x 14.7 MB does not need a ring. `devices` may name a device more
+ * than once (logical shards on one GPU; that is how the path is tested on a single-GPU box).
+ * All group calls are asynchronous except create / synchronize / download / counters; calls on one group are not
+ * re-entrant. A member failure surfaces as JT_ERR_PEER (or the member's own status) from the next blocking call. */
+typedef struct jt_group jt_group;
+typedef struct jt_group_state jt_group_state;
+typedef struct {
+  int32_t members;             /* number of member (device, scene) pairs */
+  int32_t distinct_devices;
+  int32_t peer_members;        /* members whose buffers member 0 reads through peer access (NVLink / PCIe P2P) */
+  int32_t staged_members;      /* members without peer access: copied into a staging buffer on member 0's device first */
+  int64_t reduce_bytes_remote; /* bytes read from other devices by the downloads so far */
+  int64_t downloads;
+  double stage_seconds;        /* host: flatten + wide-BVH build (once for the whole group) */
+  double upload_seconds;       /* wall time of the N parallel uploads */
+  int64_t _reserved[4];
+} jt_group_stats;
+JT_API int jt_group_create(const jt_scene_desc* desc, const int* devices, int n, jt_group** out);
+JT_API void jt_group_destroy(jt_group* group);
+JT_API int jt_group_get_stats(jt_group* group, jt_group_stats* out);
+/* The member's scene, for the parity hooks and per-device counters (borrowed: do not destroy). */
+JT_API int jt_group_scene(jt_group* group, int member, jt_scene** out);
+/* Counters summed over the members (kernel time fields: maximum over members). Blocks until the group is idle. */
+JT_API int jt_group_counters(jt_group* group, jt_counters* out, int reset);
+/* make_trace_state for the group: one sum-mode state per member + the merged host-facing bookkeeping. */
+JT_API int jt_group_state_create(jt_group* group, const jt_params* params, jt_group_state** out);
+JT_API void jt_group_state_destroy(jt_group_state* state);
+JT_API int jt_group_state_size(jt_group_state* state, int32_t* width, int32_t* height, int32_t* samples);
+JT_API int jt_group_state_reset(jt_group_state* state);
+/* trace_samples (src/trace.jl:215-274) across the group: same bookkeeping as jt_trace_samples; requests are merged
+ * until members * 512 samples are pending or a blocking call arrives, then split over the members. Returns at once. */
+JT_API int jt_group_trace_samples(jt_group* group, jt_group_state* state, const jt_params* params);
+JT_API int jt_group_trace_sample_range(jt_group* group, jt_group_state* state, const jt_params* params,
+                                       int32_t sample_begin, int32_t sample_end);
+/* Block until every member is idle; returns the first member error, if any. */
+JT_API int jt_group_synchronize(jt_group* group);
+/* Merged download: same host layouts as jt_state_download / jt_state_download_srgb8 (fused P2P reduce + finalize). */
+JT_API int jt_group_state_download(jt_group_state* state, float* image_rgba, float* albedo_rgb, float* normal_rgb,
+                                   int64_t* hits);
+JT_API int jt_group_state_download_srgb8(jt_group_state* state, uint8_t* rgba8);
 
 /* ---- host-side helpers (CPU code; the steps bvh.jl performs on the Julia host) --------------- */
 /* make_bvh (src/bvh.jl:138-183) with split_middle (:185-216) or split_sah (:218-274):

@@ -95,7 +95,8 @@ class jt_hit(C.Structure):
 
 class jt_counters(C.Structure):
     _fields_ = [("camera_paths", C.c_uint64), ("scene_rays", C.c_uint64), ("light_rays", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("_reserved", C.c_uint64 * 4)]
+                ("kernel_launches", C.c_uint64), ("extend_kernel_us", C.c_uint64),
+                ("extend_launches", C.c_uint64), ("_reserved", C.c_uint64 * 2)]
 
 
 class jt_scene_stats(C.Structure):
@@ -103,12 +104,20 @@ class jt_scene_stats(C.Structure):
                 ("prim_records", C.c_int64), ("prim_record_bytes", C.c_int64),
                 ("inlined_instances", C.c_int64), ("instanced_instances", C.c_int64),
                 ("texture_bytes", C.c_int64), ("total_device_bytes", C.c_int64),
-                ("_reserved", C.c_int64 * 8)]
+                ("wide_depth_top", C.c_int64), ("wide_depth_blas", C.c_int64), ("opened_instances", C.c_int64),
+                ("_reserved", C.c_int64 * 5)]
+
+
+class jt_group_stats(C.Structure):
+    _fields_ = [("members", C.c_int32), ("distinct_devices", C.c_int32), ("peer_members", C.c_int32),
+                ("staged_members", C.c_int32), ("reduce_bytes_remote", C.c_int64), ("downloads", C.c_int64),
+                ("stage_seconds", C.c_double), ("upload_seconds", C.c_double), ("_reserved", C.c_int64 * 4)]
 
 
 assert C.sizeof(jt_frame) == 48 and C.sizeof(jt_bvh_node) == 40 and C.sizeof(jt_instance) == 64
 assert C.sizeof(jt_material) == 104 and C.sizeof(jt_environment) == 72
-assert C.sizeof(jt_ray) == 32 and C.sizeof(jt_hit) == 32
+assert C.sizeof(jt_ray) == 32 and C.sizeof(jt_hit) == 32 and C.sizeof(jt_params) == 88
+assert C.sizeof(jt_counters) == 64 and C.sizeof(jt_scene_stats) == 128 and C.sizeof(jt_group_stats) == 80
 
 import numpy as np  # noqa: E402
 

@@ -20,6 +20,10 @@ EXPORTS = [
     "jt_state_set_samples", "jt_trace_samples", "jt_trace_sample_range", "jt_synchronize",
     "jt_elapsed_ms", "jt_intersect", "jt_intersect_instance", "jt_sample_camera",
     "jt_intersect_device", "jt_make_bvh", "jt_state_download_srgb8",
+    "jt_group_create", "jt_group_destroy", "jt_group_get_stats", "jt_group_scene", "jt_group_counters",
+    "jt_group_state_create", "jt_group_state_destroy", "jt_group_state_size", "jt_group_state_reset",
+    "jt_group_trace_samples", "jt_group_trace_sample_range", "jt_group_synchronize",
+    "jt_group_state_download", "jt_group_state_download_srgb8",
 ]
 
 
@@ -69,6 +73,22 @@ def lib() -> C.CDLL:
     L.jt_sample_camera.argtypes = [vp, C.POINTER(A.jt_params), i32, i32, vp, vp, i64, vp]
     L.jt_intersect_device.argtypes = [vp, vp, i64, C.c_int, vp]
     L.jt_make_bvh.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
+    L.jt_group_create.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.jt_group_destroy.argtypes = [vp]
+    L.jt_group_destroy.restype = None
+    L.jt_group_get_stats.argtypes = [vp, C.POINTER(A.jt_group_stats)]
+    L.jt_group_scene.argtypes = [vp, C.c_int, C.POINTER(vp)]
+    L.jt_group_counters.argtypes = [vp, C.POINTER(A.jt_counters), C.c_int]
+    L.jt_group_state_create.argtypes = [vp, C.POINTER(A.jt_params), C.POINTER(vp)]
+    L.jt_group_state_destroy.argtypes = [vp]
+    L.jt_group_state_destroy.restype = None
+    L.jt_group_state_size.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.jt_group_state_reset.argtypes = [vp]
+    L.jt_group_trace_samples.argtypes = [vp, vp, C.POINTER(A.jt_params)]
+    L.jt_group_trace_sample_range.argtypes = [vp, vp, C.POINTER(A.jt_params), i32, i32]
+    L.jt_group_synchronize.argtypes = [vp]
+    L.jt_group_state_download.argtypes = [vp, vp, vp, vp, vp]
+    L.jt_group_state_download_srgb8.argtypes = [vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("jt_device_count",):

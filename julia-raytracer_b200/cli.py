@@ -56,6 +56,9 @@ def make_parser() -> argparse.ArgumentParser:
                    choices=["wavefront", "megakernel"],
                    help="wavefront = staged kernels over compacted, material-sorted queues (default); "
                         "megakernel = one thread per pixel running the whole trace_sample")
+    p.add_argument("--gpu-devices", dest="gpu_devices", type=str, default="",
+                   help="comma-separated CUDA device ids (or 'all') to shard the sample axis over, inside one "
+                        "process (jt_group: scene replicated, fused peer-to-peer merge); empty = one device")
     return p
 
 
@@ -82,6 +85,7 @@ class Params:  # src/cli.jl:90-108
     gpu_seed: int = 0
     gpu_traversal: str = "wide"
     gpu_integrator: str = "wavefront"
+    gpu_devices: str = ""
 
     @staticmethod
     def from_args(ns: argparse.Namespace) -> "Params":

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "jt_dev_output.cuh"
 #include "jt_dev_trace.cuh"
 #include "jt_dev_wavefront.cuh"
 #include "jt_internal.h"
@@ -123,10 +124,19 @@ static int upload(jt_scene* sc, const std::vector<T>& v, const T** out) {
   return JT_OK;
 }
 
+static void state_release_device(jt_state* st);
+
 extern "C" void jt_scene_destroy(jt_scene* sc) {
   if (!sc) return;
-  for (jt_state* st : sc->states) st->has_pending = false;
   cudaSetDevice(sc->device);
+  if (sc->stream) cudaStreamSynchronize(sc->stream);
+  // states outlive their scene as orphans: their device memory goes with the scene, every later entry point on them
+  // returns JT_ERR_INVALID, and jt_state_destroy only frees the host struct
+  for (jt_state* st : sc->states) {
+    state_release_device(st);
+    st->scene = nullptr;
+  }
+  sc->states.clear();
   for (void* p : sc->allocs) cudaFree(p);
   for (int k = 0; k < 64; k++)
     if (sc->ext_ev[k]) cudaEventDestroy(sc->ext_ev[k]);
@@ -136,7 +146,7 @@ extern "C" void jt_scene_destroy(jt_scene* sc) {
   delete sc;
 }
 
-static int scene_create_impl(const jt_scene_desc* d, int device, jt_scene* sc) {
+static int scene_upload_impl(const JtStagedScene& staged, int device, jt_scene* sc) {
   int ndev = jt_device_count();
   if (ndev <= 0) return jt_set_error(JT_ERR_NO_DEVICE, "no CUDA device visible: libjtrace_b200 has no CPU fallback");
   if (device < 0 || device >= ndev) return jt_set_error(JT_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
@@ -149,10 +159,8 @@ static int scene_create_impl(const jt_scene_desc* d, int device, jt_scene* sc) {
   memset(&sc->dev, 0, sizeof(sc->dev));
   memset(&sc->stats, 0, sizeof(sc->stats));
 
-  JtStagedScene staged;
-  int rc = jt_stage_scene(d, &staged);
-  if (rc != JT_OK) return rc;
-  auto& wide = staged.wide;
+  int rc = JT_OK;
+  const auto& wide = staged.wide;
 
   // ---- upload -----------------------------------------------------------------------------------------------
   JtDevScene& D = sc->dev;
@@ -175,8 +183,8 @@ static int scene_create_impl(const jt_scene_desc* d, int device, jt_scene* sc) {
   P.wnodes = (const float4*)wn;
   P.wtris = (const float4*)wt;
   jt_fill_dev_scene(staged, P, &D);
-  sc->num_cameras = (int)d->num_cameras;
-  sc->num_instances = (int)d->num_instances;
+  sc->num_cameras = (int)staged.num_cameras;
+  sc->num_instances = (int)staged.num_instances;
   void* cnt = nullptr;
   JT_CUDA(cudaMalloc(&cnt, 8 * sizeof(unsigned long long)));
   sc->allocs.push_back(cnt);
@@ -191,20 +199,20 @@ static int scene_create_impl(const jt_scene_desc* d, int device, jt_scene* sc) {
   sc->stats.instanced_instances = wide.instanced_instances;
   sc->stats.texture_bytes = (int64_t)(staged.texels_f.size() * 16 + staged.texels_b.size() * 4);
   sc->stats.total_device_bytes = sc->device_bytes;
-  sc->stats._reserved[0] = staged.depth;
-  sc->stats._reserved[1] = staged.blas_depth;
-  sc->stats._reserved[2] = wide.flattened_instances;
+  sc->stats.wide_depth_top = staged.depth;
+  sc->stats.wide_depth_blas = staged.blas_depth;
+  sc->stats.opened_instances = wide.flattened_instances;
   return JT_OK;
 }
 
-extern "C" int jt_scene_create(const jt_scene_desc* desc, int device, jt_scene** out) {
-  if (!desc || !out) return jt_set_error(JT_ERR_INVALID, "jt_scene_create: null argument");
+// Upload an already staged scene (host vectors, wide BVH built) to `device`. jt_group stages once and uploads N times.
+int jt_scene_create_staged(const JtStagedScene& staged, int device, jt_scene** out) {
   *out = nullptr;
   jt_scene* sc = new (std::nothrow) jt_scene();
   if (!sc) return jt_set_error(JT_ERR_INTERNAL, "out of host memory");
   int rc;
   try {
-    rc = scene_create_impl(desc, device, sc);
+    rc = scene_upload_impl(staged, device, sc);
   } catch (const std::exception& e) {
     rc = jt_set_error(JT_ERR_INTERNAL, "jt_scene_create: %s", e.what());
   } catch (...) {
@@ -218,6 +226,28 @@ extern "C" int jt_scene_create(const jt_scene_desc* desc, int device, jt_scene**
   }
   *out = sc;
   return JT_OK;
+}
+
+int jt_stage_scene_checked(const jt_scene_desc* desc, JtStagedScene* staged) {
+  try {
+    return jt_stage_scene(desc, staged);
+  } catch (const std::exception& e) {
+    return jt_set_error(JT_ERR_INTERNAL, "jt_scene_create: %s", e.what());
+  } catch (...) {
+    return jt_set_error(JT_ERR_INTERNAL, "jt_scene_create: unknown exception");
+  }
+}
+
+extern "C" int jt_scene_create(const jt_scene_desc* desc, int device, jt_scene** out) {
+  if (!desc || !out) return jt_set_error(JT_ERR_INVALID, "jt_scene_create: null argument");
+  *out = nullptr;
+  int ndev = jt_device_count();  // before the (expensive) staging
+  if (ndev <= 0) return jt_set_error(JT_ERR_NO_DEVICE, "no CUDA device visible: libjtrace_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return jt_set_error(JT_ERR_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+  JtStagedScene staged;
+  int rc = jt_stage_scene_checked(desc, &staged);
+  if (rc != JT_OK) return rc;
+  return jt_scene_create_staged(staged, device, out);
 }
 
 extern "C" int jt_scene_get_stats(jt_scene* sc, jt_scene_stats* out) {
@@ -239,8 +269,8 @@ extern "C" int jt_scene_counters(jt_scene* sc, jt_counters* out, int reset) {
   out->scene_rays = h[1];
   out->light_rays = h[2];
   out->kernel_launches = sc->launches;
-  out->_reserved[0] = (uint64_t)(sc->extend_ms * 1000.0);  // microseconds in the extend (closest-hit) kernel
-  out->_reserved[1] = sc->extend_launches;
+  out->extend_kernel_us = (uint64_t)(sc->extend_ms * 1000.0);  // microseconds in the extend (closest-hit) kernel
+  out->extend_launches = sc->extend_launches;
   if (reset) {
     JT_CUDA(cudaMemset(sc->d_counters, 0, sizeof(h)));
     sc->launches = 0;
@@ -392,24 +422,12 @@ __global__ void k_finalize(const float4* __restrict__ image, const float4* __res
   if (out_hits) out_hits[i] = hits[i];
 }
 
-// N3: the save path on the GPU. rgb_to_srgb (src/color.jl:25-29) + clamp01nan + 8-bit quantisation
-// of save_image (src/sceneio.jl:97-113). Julia's `^(rgb, 1/2.4f0)` is Float32(exp2(log2(Float64(x)) * Float64(y))).
+// N3: the save path on the GPU (per-pixel conversion in jt_dev_output.cuh).
 __global__ void k_srgb8(const float4* __restrict__ image, long long n, float scale, uchar4* __restrict__ out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = image[i];
-  float c[4] = {p.x * scale, p.y * scale, p.z * scale, p.w * scale};
-  unsigned char b[4];
-  const double expo = (double)(1.0f / 2.4f);
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    float v = c[k];
-    if (k < 3) v = (v <= 0.0031308f) ? 12.92f * v : 1.055f * (float)exp2(log2((double)v) * expo) - 0.055f;
-    if (!(v == v)) v = 0.0f;              // clamp01nan: NaN -> 0
-    v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
-    b[k] = (unsigned char)__float2int_rn(v * 255.0f);
-  }
-  out[i] = make_uchar4(b[0], b[1], b[2], b[3]);
+  out[i] = jt_srgb8_pixel(make_float4(p.x * scale, p.y * scale, p.z * scale, p.w * scale));
 }
 
 // =================================================================================================
@@ -423,6 +441,10 @@ static int check_params(jt_scene* sc, const jt_params* p) {
   if (p->traversal != 0 && p->traversal != 1) return jt_set_error(JT_ERR_INVALID, "traversal must be 0 (wide) or 1 (reference)");
   if (p->accumulate != 0 && p->accumulate != 1) return jt_set_error(JT_ERR_INVALID, "accumulate must be 0 or 1");
   if (p->integrator != 0 && p->integrator != 1) return jt_set_error(JT_ERR_INVALID, "integrator must be 0 (wavefront) or 1 (megakernel)");
+  // the wavefront integrator packs bounce + 1 into 8 bits of the per-slot control word (jt_dev_wavefront.cuh) and always
+  // traces the camera segment; outside 0..254 it would silently diverge from the reference loop `for bounce in 0:bounces`
+  if (p->integrator == 0 && (p->bounces < 0 || p->bounces > 254))
+    return jt_set_error(JT_ERR_INVALID, "bounces %d outside 0..254 (wavefront integrator; integrator = 1 accepts any value)", p->bounces);
   if (p->sampler == 1 && sc->dev.num_lights == 0)
     return jt_set_error(JT_ERR_UNSUPPORTED, "path sampler on a scene without lights: sample_lights indexes an empty array in the reference");
   return JT_OK;
@@ -465,8 +487,14 @@ extern "C" int jt_state_create(jt_scene* sc, const jt_params* p, jt_state** out)
   return jt_state_reset(st);
 }
 
+#define JT_LIVE_STATE(st, who)                                                                    \
+  do {                                                                                           \
+    if (!(st)) return jt_set_error(JT_ERR_INVALID, who ": null argument");                       \
+    if (!(st)->scene) return jt_set_error(JT_ERR_INVALID, who ": the state's scene was destroyed"); \
+  } while (0)
+
 extern "C" int jt_state_reset(jt_state* st) {
-  if (!st) return jt_set_error(JT_ERR_INVALID, "jt_state_reset: null argument");
+  JT_LIVE_STATE(st, "jt_state_reset");
   jt_scene* sc = st->scene;
   st->has_pending = false;
   JT_CUDA(cudaSetDevice(sc->device));
@@ -479,29 +507,46 @@ extern "C" int jt_state_reset(jt_state* st) {
   return JT_OK;
 }
 
-extern "C" void jt_state_destroy(jt_state* st) {
-  if (!st) return;
+// Frees everything the state owns on the device (the caller has made the scene's device current and idle).
+static void state_release_device(jt_state* st) {
   st->has_pending = false;
-  auto& v = st->scene->states;
-  for (size_t i = 0; i < v.size(); i++)
-    if (v[i] == st) {
-      v.erase(v.begin() + (long)i);
-      break;
-    }
-  cudaSetDevice(st->scene->device);
-  cudaStreamSynchronize(st->scene->stream);
   cudaFree(st->dev.image); cudaFree(st->dev.albedo); cudaFree(st->dev.normal); cudaFree(st->dev.hits);
+  st->dev.image = st->dev.albedo = st->dev.normal = nullptr;
+  st->dev.hits = nullptr;
   for (void* p : st->wf_allocs) cudaFree(p);
+  st->wf_allocs.clear();
+  st->wf_ready = false;
   for (int k = 1; k < JT_MAX_PIPES; k++)
     if (st->pipe_stream[k]) cudaStreamDestroy(st->pipe_stream[k]);
-  for (int k = 0; k < JT_MAX_PIPES; k++)
+  for (int k = 0; k < JT_MAX_PIPES; k++) {
+    st->pipe_stream[k] = nullptr;
     if (st->pipe_done[k]) cudaEventDestroy(st->pipe_done[k]);
-  for (int k = 0; k < JT_MAX_PIPES; k++)
-    for (int b = 0; b < 2; b++)
+    st->pipe_done[k] = nullptr;
+    for (int b = 0; b < 2; b++) {
       if (st->poll_ev[b][k]) cudaEventDestroy(st->poll_ev[b][k]);
+      st->poll_ev[b][k] = nullptr;
+    }
+  }
   if (st->h_counts) cudaFreeHost(st->h_counts);
   if (st->d_pack) cudaFree(st->d_pack);
   if (st->h_pack) cudaFreeHost(st->h_pack);
+  st->h_counts = nullptr;
+  st->d_pack = st->h_pack = nullptr;
+}
+
+extern "C" void jt_state_destroy(jt_state* st) {
+  if (!st) return;
+  if (st->scene) {  // an orphan (scene destroyed first) has nothing left on the device
+    auto& v = st->scene->states;
+    for (size_t i = 0; i < v.size(); i++)
+      if (v[i] == st) {
+        v.erase(v.begin() + (long)i);
+        break;
+      }
+    cudaSetDevice(st->scene->device);
+    cudaStreamSynchronize(st->scene->stream);
+    state_release_device(st);
+  }
   delete st;
 }
 
@@ -521,9 +566,13 @@ extern "C" int jt_state_set_samples(jt_state* st, int32_t samples) {
 
 extern "C" int jt_state_device_buffers(jt_state* st, void** image, void** albedo, void** normal, void** hits,
                                        int64_t* count) {
-  if (!st) return jt_set_error(JT_ERR_INVALID, "jt_state_device_buffers: null argument");
+  JT_LIVE_STATE(st, "jt_state_device_buffers");
+  JT_CUDA(cudaSetDevice(st->scene->device));
   int frc = flush_state(st);
   if (frc) return frc;
+  // the caller reduces these buffers on ITS stream (NCCL / torch): everything the library enqueued must have landed.
+  // (The pipelines' streams are joined into scene->stream at the end of every flushed range.)
+  JT_CUDA(cudaStreamSynchronize(st->scene->stream));
   if (image) *image = st->dev.image;
   if (albedo) *albedo = st->dev.albedo;
   if (normal) *normal = st->dev.normal;
@@ -533,7 +582,7 @@ extern "C" int jt_state_device_buffers(jt_state* st, void** image, void** albedo
 }
 
 extern "C" int jt_state_download(jt_state* st, float* image, float* albedo, float* normal, int64_t* hits) {
-  if (!st) return jt_set_error(JT_ERR_INVALID, "jt_state_download: null argument");
+  JT_LIVE_STATE(st, "jt_state_download");
   jt_scene* sc = st->scene;
   JT_CUDA(cudaSetDevice(sc->device));
   int frc = flush_state(st);
@@ -568,7 +617,8 @@ extern "C" int jt_state_download(jt_state* st, float* image, float* albedo, floa
 }
 
 extern "C" int jt_state_download_srgb8(jt_state* st, uint8_t* rgba8) {
-  if (!st || !rgba8) return jt_set_error(JT_ERR_INVALID, "jt_state_download_srgb8: null argument");
+  if (!rgba8) return jt_set_error(JT_ERR_INVALID, "jt_state_download_srgb8: null argument");
+  JT_LIVE_STATE(st, "jt_state_download_srgb8");
   jt_scene* sc = st->scene;
   JT_CUDA(cudaSetDevice(sc->device));
   int frc = flush_state(st);

@@ -126,7 +126,9 @@ JT_DEV WfPath wf_load_ctl(const WfBuffers& B, int s) {
   return p;
 }
 JT_DEV void wf_store_ctl(const WfBuffers& B, int s, const WfPath& p) {
-  B.ctl[s] = make_uint4(p.sample, p.draw, (unsigned)(p.bounce + 1) | ((unsigned)p.opbounce << 8) | (p.flags << 16),
+  // 8 bits each for bounce + 1 and opbounce (check_params bounds bounces to 0..254 for this integrator; opbounce <= 129)
+  B.ctl[s] = make_uint4(p.sample, p.draw,
+                        ((unsigned)(p.bounce + 1) & 0xFFu) | (((unsigned)p.opbounce & 0xFFu) << 8) | (p.flags << 16),
                         __float_as_uint(p.max_roughness));
 }
 

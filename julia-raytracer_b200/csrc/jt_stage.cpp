@@ -71,6 +71,36 @@ static void pack_ref_nodes(const jt_bvh_node* nodes, int64_t n, int32_t child_of
   }
 }
 
+// Validate a host-built reference tree before it is walked by MODE_REF with its fixed int stack[JT_REF_STACK]
+// (jt_dev_traverse.cuh): children and leaf ranges in range, every node reachable at most once from the root, and the
+// traversal stack high-water mark (an internal node pops one entry and pushes two) within the stack. The reference
+// raises BoundsError for the same inputs.
+#define JT_REF_STACK_LIMIT 128 /* == JT_REF_STACK */
+static int validate_ref_tree(const jt_bvh_node* nodes, int64_t n, int64_t num_prims, const char* what, long long id) {
+  if (n <= 0) return JT_OK;
+  std::vector<std::pair<int64_t, int>> st;  // node, stack entries below it while it is being visited
+  st.push_back({0, 0});
+  int64_t visited = 0;
+  while (!st.empty()) {
+    auto [i, below] = st.back();
+    st.pop_back();
+    if (++visited > n) return jt_set_error(JT_ERR_INVALID, "%s %lld: BVH is not a tree (a node is reachable twice)", what, id);
+    const jt_bvh_node& b = nodes[i];
+    if (b.internal) {
+      if (b.axis < 1 || b.axis > 3) return jt_set_error(JT_ERR_INVALID, "%s %lld: BVH node %lld has axis %d", what, id, (long long)i, (int)b.axis);
+      if (b.start < 1 || b.start + 1 > n) return jt_set_error(JT_ERR_INVALID, "%s %lld: BVH node %lld child index out of range", what, id, (long long)i);
+      if (below + 2 > JT_REF_STACK_LIMIT)
+        return jt_set_error(JT_ERR_UNSUPPORTED, "%s %lld: BVH too deep for the reference-order traversal stack (%d entries, --bvhstacksize default)", what, id, JT_REF_STACK_LIMIT);
+      st.push_back({b.start - 1, below + 1});  // the child visited first still has its sibling below it
+      st.push_back({b.start, below + 1});
+    } else {
+      if (b.num < 0 || b.start < 1 || b.start - 1 + b.num > num_prims)
+        return jt_set_error(JT_ERR_INVALID, "%s %lld: BVH leaf %lld primitive range out of bounds", what, id, (long long)i);
+    }
+  }
+  return JT_OK;
+}
+
 static int max_wide_depth(const std::vector<JtWideNode>& nodes, int root) {
   if (root < 0) return 0;
   int best = 0;
@@ -152,6 +182,7 @@ int jt_stage_scene(const jt_scene_desc* d, JtStagedScene* S) {
 
   // ---- shapes: geometry arrays + reference BVHs --------------------------------------------------
   // TLAS first
+  if (int vrc = validate_ref_tree(d->bvh.nodes, d->bvh.num_nodes, d->bvh.num_primitives, "scene", 0)) return vrc;
   pack_ref_nodes(d->bvh.nodes, d->bvh.num_nodes, 0, 0, &ref_nodes);
   for (int64_t i = 0; i < d->bvh.num_primitives; i++) {
     int64_t p = d->bvh.primitives[i];
@@ -214,6 +245,7 @@ int jt_stage_scene(const jt_scene_desc* d, JtStagedScene* S) {
       R.ref_node_off = (int32_t)(ref_nodes.size() / 2);
       R.ref_prim_off = (int32_t)ref_prims.size();
       R.num_ref_nodes = (int32_t)h.bvh.num_nodes;
+      if (int vrc = validate_ref_tree(h.bvh.nodes, h.bvh.num_nodes, ne, "shape", (long long)s)) return vrc;
       pack_ref_nodes(h.bvh.nodes, h.bvh.num_nodes, 0, 0, &ref_nodes);  // shape-local indices
       for (int64_t i = 0; i < ne; i++) {
         int64_t p = h.bvh.primitives[i];

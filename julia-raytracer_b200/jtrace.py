@@ -13,7 +13,8 @@ from .cli import Params, parse_cli_args
 from .lights import make_trace_lights
 from .scene import find_camera
 from .sceneio import load_scene, save_image, save_srgb8  # noqa: F401
-from .trace import DeviceScene, get_image, make_trace_state, trace_samples
+from . import _lib
+from .trace import DeviceGroup, DeviceScene, get_image, make_trace_state, trace_samples
 
 
 def format_seconds(seconds: float) -> str:
@@ -30,7 +31,19 @@ def format_seconds(seconds: float) -> str:
     return f"{hours:02d}:{minutes:02d}:{i_seconds:02d}.{ms:03d}"
 
 
-def main(params: Union[str, Params, None], device: int = 0) -> Optional[dict]:
+def parse_devices(spec) -> list:
+    """'' -> [], 'all' -> every visible device, '0,2,3' -> [0, 2, 3]; lists pass through."""
+    if isinstance(spec, (list, tuple)):
+        return [int(d) for d in spec]
+    spec = str(spec).strip()
+    if spec == "":
+        return []
+    if spec == "all":
+        return list(range(_lib.lib().jt_device_count()))
+    return [int(x) for x in spec.split(",") if x.strip() != ""]
+
+
+def main(params: Union[str, Params, None], device: int = 0, devices=None) -> Optional[dict]:
     if isinstance(params, str):
         params = parse_cli_args(params)
     if params is None:
@@ -61,7 +74,12 @@ def main(params: Union[str, Params, None], device: int = 0) -> Optional[dict]:
     lights = make_trace_lights(scene, params)
     print("uploading scene to the GPU...")
     t0 = time.time()
-    dscene = DeviceScene(scene, bvh, lights, device)
+    devs = parse_devices(devices if devices is not None else getattr(params, "gpu_devices", ""))
+    if len(devs) > 1:  # one host thread, N devices: the sample axis is sharded inside the library (jt_group)
+        dscene = DeviceGroup(scene, bvh, lights, devs)
+        print(f"    sharding samples over devices {devs}")
+    else:
+        dscene = DeviceScene(scene, bvh, lights, devs[0] if devs else device)
     print(f"uploaded in {format_seconds(time.time() - t0)}")
     print("making state...")
     state = make_trace_state(dscene, params)

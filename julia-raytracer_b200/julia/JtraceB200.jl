@@ -1,11 +1,17 @@
 #=
 JtraceB200: ccall glue between julia-raytracer's host code and libjtrace_b200.so.
 
-The Julia host keeps loading the scene (sceneio.jl), building the BVH (bvh.jl) and the lights
-(trace.jl:117); this module adds the flattening pass and replaces ONE function of the hot path:
+The Julia host keeps loading the scene (sceneio.jl), building the BVH (bvh.jl), the lights
+(trace.jl:117) and the TraceState (trace.jl:189); this module adds the flattening pass and ONE new
+method of the hot-path function, selected by dispatch on the type of its `scene` argument:
 
-    trace_samples(state, scene, bvh, lights, params, bvh_stacks, bvh_sub_stacks, volume_stacks)
+    trace_samples(state::TraceState, scene::GpuScene, bvh, lights, params, bvh_stacks, bvh_sub_stacks, volume_stacks)
                                                                               (src/trace.jl:215-224)
+
+`state` stays the reference's own TraceState: `state.samples` advances exactly like the reference's
+(src/trace.jl:225-232, read by the progress print at src/jtrace.jl:96-105), and its image / albedo /
+normal / hits vectors are refreshed from the device on the final call, so `get_image(state)`
+(src/trace.jl:676) and `save_image` run unchanged. INTEGRATION.md has the diff of src/jtrace.jl.
 
 NOTE: written without a Julia toolchain at hand (none in the build image, no network). Struct layouts
 follow SURVEY.md Appendix B; `check_layouts()` asserts them against `sizeof`/`fieldoffset` on first use.
@@ -19,6 +25,7 @@ using ..Scene: SceneData, CameraData, InstanceData, MaterialData, EnvironmentDat
 using ..Shape: ShapeData
 using ..Bvh: SceneBvh, BvhNode, BvhTree
 using ..Trace: TraceLights, TraceLight, TraceState
+import ..Trace: trace_samples          # extended with a method for GpuScene below
 using ..Color: srgb_to_rgb
 using ..Cli: Params
 
@@ -103,19 +110,44 @@ function check_layouts()
     @assert sizeof(EnvironmentData) == 72 && fieldoffset(EnvironmentData, 3) == 64
     @assert sizeof(Frame3f) == 48 && sizeof(Vec4f) == 16 && sizeof(Vec4b) == 4
     @assert sizeof(JtParams) == 88 && sizeof(JtBvhDesc) == 32 && sizeof(JtShapeDesc) == 128
+    @assert sizeof(JtTextureDesc) == 40 && sizeof(JtLightDesc) == 32 && sizeof(JtCamera) == 72
+    @assert sizeof(JtSceneDesc) == 152
 end
 
 check(rc) = rc == 0 || error("libjtrace_b200: ", unsafe_string(ccall((:jt_last_error, LIB), Cstring, ())))
 
-# ---- the new flattening pass ------------------------------------------------------------------------
+# ---- the new flattening pass + the device twin of the TraceState --------------------------------------
 mutable struct GpuScene
-    h::Ptr{Cvoid}
-    keep::Vector{Any}    # everything the description pointed into (alive until the upload returned)
+    h::Ptr{Cvoid}          # jt_scene* (one device) or jt_group* (several devices, sharded inside the library)
+    state::Ptr{Cvoid}      # jt_state* / jt_group_state*: device twin of the host TraceState
+    grouped::Bool
+    host::TraceState       # the reference's own state: refreshed by sync!
 end
 
 ptr_or_null(v::Vector{T}) where {T} = isempty(v) ? Ptr{T}(C_NULL) : pointer(v)
 
-function gpu_scene(scene::SceneData, bvh::SceneBvh, lights::TraceLights; device::Integer = 0)::GpuScene
+function destroy!(g::GpuScene)
+    if g.grouped
+        g.state != C_NULL && ccall((:jt_group_state_destroy, LIB), Cvoid, (Ptr{Cvoid},), g.state)
+        g.h != C_NULL && ccall((:jt_group_destroy, LIB), Cvoid, (Ptr{Cvoid},), g.h)
+    else
+        g.state != C_NULL && ccall((:jt_state_destroy, LIB), Cvoid, (Ptr{Cvoid},), g.state)
+        g.h != C_NULL && ccall((:jt_scene_destroy, LIB), Cvoid, (Ptr{Cvoid},), g.h)
+    end
+    g.state = C_NULL
+    g.h = C_NULL
+    nothing
+end
+
+"""
+    gpu_scene(scene, bvh, lights, state, params; devices = [0], traversal = 0, seed = 0)
+
+Flatten (scene, bvh, lights) into the C description, upload it (replicated on every device of `devices`)
+and create the device twin of `state` (the TraceState `make_trace_state` returned). Called once, after
+`make_trace_state` (src/jtrace.jl:69). The library copies everything before returning.
+"""
+function gpu_scene(scene::SceneData, bvh::SceneBvh, lights::TraceLights, state::TraceState, params::Params;
+                   devices::Vector{<:Integer} = [0], traversal::Integer = 0, seed::Integer = 0)::GpuScene
     check_layouts()
     cams = [JtCamera(c) for c in scene.cameras]
     # vertex index vectors are Vector{SVector{k,Int64}}: reinterpret as flat Int64
@@ -138,50 +170,69 @@ function gpu_scene(scene::SceneData, bvh::SceneBvh, lights::TraceLights; device:
         length(texs), ptr_or_null(texs), length(scene.materials), ptr_or_null(scene.materials),
         length(lts), ptr_or_null(lts), JtBvhDesc(bvh.bvh), pointer(lut))
     h = Ref{Ptr{Cvoid}}(C_NULL)
+    st = Ref{Ptr{Cvoid}}(C_NULL)
+    jp = JtParams(params; traversal = traversal, seed = seed)
     keep = Any[scene, bvh, lights, cams, shapes, texs, lts, lut]
-    GC.@preserve keep check(ccall((:jt_scene_create, LIB), Cint, (Ref{JtSceneDesc}, Cint, Ref{Ptr{Cvoid}}),
-                                  desc, device, h))
-    g = GpuScene(h[], Any[])
-    finalizer(x -> ccall((:jt_scene_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), g)
+    grouped = length(devices) > 1
+    if grouped
+        devs = Cint[d for d in devices]
+        GC.@preserve keep devs check(ccall((:jt_group_create, LIB), Cint,
+            (Ref{JtSceneDesc}, Ptr{Cint}, Cint, Ref{Ptr{Cvoid}}), desc, devs, length(devs), h))
+        check(ccall((:jt_group_state_create, LIB), Cint, (Ptr{Cvoid}, Ref{JtParams}, Ref{Ptr{Cvoid}}), h[], jp, st))
+    else
+        GC.@preserve keep check(ccall((:jt_scene_create, LIB), Cint, (Ref{JtSceneDesc}, Cint, Ref{Ptr{Cvoid}}),
+                                      desc, devices[1], h))
+        check(ccall((:jt_state_create, LIB), Cint, (Ptr{Cvoid}, Ref{JtParams}, Ref{Ptr{Cvoid}}), h[], jp, st))
+    end
+    g = GpuScene(h[], st[], grouped, state)
+    w = Ref{Int32}(0); ht = Ref{Int32}(0)
+    if grouped
+        check(ccall((:jt_group_state_size, LIB), Cint, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}, Ptr{Int32}), g.state, w, ht, C_NULL))
+    else
+        check(ccall((:jt_state_size, LIB), Cint, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}, Ptr{Int32}), g.state, w, ht, C_NULL))
+    end
+    @assert (w[], ht[]) == (state.width, state.height)     # make_trace_state's sizes (src/trace.jl:189-197)
+    finalizer(destroy!, g)
     g
 end
 
-# ---- TraceState with a device twin --------------------------------------------------------------------
-mutable struct GpuState
-    host::TraceState          # the reference's own struct: image / albedo / normal / hits / samples
-    h::Ptr{Cvoid}
-    scene::GpuScene
-end
-
-function gpu_state(g::GpuScene, make_trace_state::Function, scene::SceneData, params::Params)::GpuState
-    host = make_trace_state(scene, params)            # src/trace.jl:189-213 (sizes + zeroed buffers)
-    h = Ref{Ptr{Cvoid}}(C_NULL)
-    check(ccall((:jt_state_create, LIB), Cint, (Ptr{Cvoid}, Ref{JtParams}, Ref{Ptr{Cvoid}}), g.h, JtParams(params), h))
-    st = GpuState(host, h[], g)
-    finalizer(x -> ccall((:jt_state_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h), st)
-    st
-end
-
-function sync!(st::GpuState)
-    s = st.host
-    GC.@preserve s check(ccall((:jt_state_download, LIB), Cint,
-        (Ptr{Cvoid}, Ptr{Vec4f}, Ptr{Vec3f}, Ptr{Vec3f}, Ptr{Int64}),
-        st.h, pointer(s.image), pointer(s.albedo), pointer(s.normal), pointer(s.hits)))
-    st
+"Refresh the host TraceState (image / albedo / normal / hits, the reference's layouts) from the device."
+function sync!(g::GpuScene)
+    s = g.host
+    GC.@preserve s begin
+        if g.grouped
+            check(ccall((:jt_group_state_download, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Vec4f}, Ptr{Vec3f}, Ptr{Vec3f}, Ptr{Int64}),
+                g.state, pointer(s.image), pointer(s.albedo), pointer(s.normal), pointer(s.hits)))
+        else
+            check(ccall((:jt_state_download, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Vec4f}, Ptr{Vec3f}, Ptr{Vec3f}, Ptr{Int64}),
+                g.state, pointer(s.image), pointer(s.albedo), pointer(s.normal), pointer(s.hits)))
+        end
+    end
+    g
 end
 
 """
-    trace_samples(state, scene, bvh, lights, params, bvh_stacks, bvh_sub_stacks, volume_stacks)
+    trace_samples(state, scene::GpuScene, bvh, lights, params, bvh_stacks, bvh_sub_stacks, volume_stacks)
 
-Drop-in for `Trace.trace_samples` (src/trace.jl:215-274): `state` is a `GpuState`; `scene`, `bvh`,
-`lights` already live on the device inside `state.scene`; the scratch stacks are ignored.
+The GPU method of `Trace.trace_samples` (src/trace.jl:215-274): same arguments in the same order; `bvh`,
+`lights` and the three scratch stacks are ignored (they already live on the device / are not needed).
+Enqueues `params.batch` more samples per pixel and returns; on the call that reaches `params.samples`
+the host arrays of `state` are refreshed.
 """
-function trace_samples(st::GpuState, scene, bvh, lights, params::Params, bvh_stacks = nothing,
+function trace_samples(state::TraceState, g::GpuScene, bvh, lights, params::Params, bvh_stacks = nothing,
                        bvh_sub_stacks = nothing, volume_stacks = nothing)
-    st.host.samples >= params.samples && return
-    check(ccall((:jt_trace_samples, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{JtParams}), st.scene.h, st.h, JtParams(params)))
-    st.host.samples = min(st.host.samples + params.batch, params.samples)
-    st.host.samples == params.samples && sync!(st)       # get_image(state.host) then works unchanged
+    state === g.host || error("JtraceB200.trace_samples: `state` is not the TraceState given to gpu_scene")
+    state.samples >= params.samples && return            # src/trace.jl:225-227
+    jp = JtParams(params)
+    if g.grouped
+        check(ccall((:jt_group_trace_samples, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{JtParams}), g.h, g.state, jp))
+    else
+        check(ccall((:jt_trace_samples, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{JtParams}), g.h, g.state, jp))
+    end
+    state.samples = min(state.samples + max(params.batch, 1), params.samples)   # src/trace.jl:228-232
+    state.samples == params.samples && sync!(g)
     nothing
 end
 

@@ -33,6 +33,12 @@ def to_jt_params(params: Params, accumulate: int = 0) -> A.jt_params:
     return p
 
 
+def _counters_dict(c: A.jt_counters) -> dict:
+    return dict(camera_paths=int(c.camera_paths), scene_rays=int(c.scene_rays),
+                light_rays=int(c.light_rays), kernel_launches=int(c.kernel_launches),
+                extend_us=int(c.extend_kernel_us), extend_launches=int(c.extend_launches))
+
+
 class DeviceScene:
     """(scene, bvh, lights) resident on one GPU: what `trace_samples` consumes."""
 
@@ -44,11 +50,26 @@ class DeviceScene:
         self.h = h
         self.device = device
         self.scene = scene
+        self._states = []
+        self._owned = True
+
+    @classmethod
+    def borrowed(cls, handle, device: int, scene: SceneData) -> "DeviceScene":
+        """A member scene of a DeviceGroup (owned by the group): parity hooks and per-device counters."""
+        self = cls.__new__(cls)
+        self.L = _lib.lib()
+        self.flat = None
+        self.h, self.device, self.scene = handle, device, scene
+        self._states, self._owned = [], False
+        return self
 
     def close(self):
-        if getattr(self, "h", None):
+        # states first (the library also tolerates the other order: they become orphans)
+        for st in list(getattr(self, "_states", [])):
+            st.close()
+        if getattr(self, "h", None) and getattr(self, "_owned", True):
             self.L.jt_scene_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -59,16 +80,12 @@ class DeviceScene:
     def stats(self) -> dict:
         s = A.jt_scene_stats()
         _lib.check(self.L.jt_scene_get_stats(self.h, C.byref(s)))
-        d = {k: int(getattr(s, k)) for k, _ in A.jt_scene_stats._fields_ if k != "_reserved"}
-        d["wide_depth_top"], d["wide_depth_blas"] = int(s._reserved[0]), int(s._reserved[1])
-        return d
+        return {k: int(getattr(s, k)) for k, _ in A.jt_scene_stats._fields_ if k != "_reserved"}
 
     def counters(self, reset: bool = False) -> dict:
         c = A.jt_counters()
         _lib.check(self.L.jt_scene_counters(self.h, C.byref(c), int(reset)))
-        return dict(camera_paths=int(c.camera_paths), scene_rays=int(c.scene_rays),
-                    light_rays=int(c.light_rays), kernel_launches=int(c.kernel_launches),
-                    extend_us=int(c._reserved[0]), extend_launches=int(c._reserved[1]))
+        return _counters_dict(c)
 
     def synchronize(self):
         _lib.check(self.L.jt_synchronize(self.h))
@@ -112,6 +129,7 @@ class TraceState:
         h = C.c_void_p()
         _lib.check(self.L.jt_state_create(dscene.h, C.byref(self.jp), C.byref(h)))
         self.h = h
+        dscene._states.append(self)
         w, hh, s = C.c_int32(), C.c_int32(), C.c_int32()
         _lib.check(self.L.jt_state_size(self.h, C.byref(w), C.byref(hh), C.byref(s)))
         self.width, self.height = w.value, hh.value
@@ -155,6 +173,116 @@ class TraceState:
         if getattr(self, "h", None):
             self.L.jt_state_destroy(self.h)
             self.h = None
+            try:
+                self.dscene._states.remove(self)
+            except ValueError:
+                pass
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceGroup:
+    """(scene, bvh, lights) replicated on several GPUs behind ONE host thread (jt_group): the scene is
+    staged once, every device gets a worker thread, sample ranges are split over the members and the download merges
+    the members' sum buffers with one fused peer-to-peer reduce + finalize kernel on the first device."""
+
+    def __init__(self, scene: SceneData, bvh: SceneBvh, lights: List[TraceLight], devices):
+        self.L = _lib.lib()
+        self.flat = FlatScene(scene, bvh, lights)
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        _lib.check(self.L.jt_group_create(self.flat.byref(), arr, len(self.devices), C.byref(h)))
+        self.h = h
+        self.scene = scene
+        self._states = []
+
+    def member(self, k: int) -> DeviceScene:
+        h = C.c_void_p()
+        _lib.check(self.L.jt_group_scene(self.h, k, C.byref(h)))
+        return DeviceScene.borrowed(h, self.devices[k], self.scene)
+
+    def stats(self) -> dict:
+        s = A.jt_group_stats()
+        _lib.check(self.L.jt_group_get_stats(self.h, C.byref(s)))
+        d = {k: getattr(s, k) for k, _ in A.jt_group_stats._fields_ if k != "_reserved"}
+        d["scene"] = self.member(0).stats()
+        return d
+
+    def counters(self, reset: bool = False) -> dict:
+        c = A.jt_counters()
+        _lib.check(self.L.jt_group_counters(self.h, C.byref(c), int(reset)))
+        return _counters_dict(c)
+
+    def synchronize(self):
+        _lib.check(self.L.jt_group_synchronize(self.h))
+
+    def close(self):
+        for st in list(getattr(self, "_states", [])):
+            st.close()
+        if getattr(self, "h", None):
+            self.L.jt_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GroupState:
+    """TraceState of a DeviceGroup: same host arrays, merged on download."""
+
+    def __init__(self, group: DeviceGroup, params: Params):
+        self.dscene = group
+        self.L = group.L
+        self.jp = to_jt_params(params, 1)
+        h = C.c_void_p()
+        _lib.check(self.L.jt_group_state_create(group.h, C.byref(self.jp), C.byref(h)))
+        self.h = h
+        group._states.append(self)
+        w, hh = C.c_int32(), C.c_int32()
+        _lib.check(self.L.jt_group_state_size(self.h, C.byref(w), C.byref(hh), None))
+        self.width, self.height = w.value, hh.value
+        n = self.width * self.height
+        self.image = np.zeros((n, 4), np.float32)
+        self.albedo = np.zeros((n, 3), np.float32)
+        self.normal = np.zeros((n, 3), np.float32)
+        self.hits = np.zeros(n, np.int64)
+        self.denoised = np.zeros((0, 4), np.float32)
+
+    @property
+    def samples(self) -> int:
+        s = C.c_int32()
+        _lib.check(self.L.jt_group_state_size(self.h, None, None, C.byref(s)))
+        return s.value
+
+    def sync(self) -> "GroupState":
+        _lib.check(self.L.jt_group_state_download(self.h, self.image.ctypes.data, self.albedo.ctypes.data,
+                                                  self.normal.ctypes.data, self.hits.ctypes.data))
+        return self
+
+    def srgb8(self) -> np.ndarray:
+        out = np.zeros((self.height, self.width, 4), np.uint8)
+        _lib.check(self.L.jt_group_state_download_srgb8(self.h, out.ctypes.data))
+        return out
+
+    def reset(self):
+        _lib.check(self.L.jt_group_state_reset(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.jt_group_state_destroy(self.h)
+            self.h = None
+            try:
+                self.dscene._states.remove(self)
+            except ValueError:
+                pass
 
     def __del__(self):
         try:
@@ -165,6 +293,8 @@ class TraceState:
 
 def make_trace_state(dscene: DeviceScene, params: Params, accumulate: int = 0) -> TraceState:
     """src/trace.jl:189-213 (sizes from resolution and the camera aspect; zeroed buffers)."""
+    if isinstance(dscene, DeviceGroup):
+        return GroupState(dscene, params)
     return TraceState(dscene, params, accumulate)
 
 
@@ -174,7 +304,10 @@ def trace_samples(state: TraceState, scene: DeviceScene, bvh=None, lights=None, 
     scratch stacks are ignored. Enqueues `params.batch` more samples per pixel and returns."""
     jp = to_jt_params(params, state.jp.accumulate) if params is not None else state.jp
     L = state.L
-    _lib.check(L.jt_trace_samples(scene.h, state.h, C.byref(jp)))
+    if isinstance(state, GroupState):
+        _lib.check(L.jt_group_trace_samples(scene.h, state.h, C.byref(jp)))
+    else:
+        _lib.check(L.jt_trace_samples(scene.h, state.h, C.byref(jp)))
     if state.samples >= jp.samples:
         state.sync()
 
@@ -182,7 +315,10 @@ def trace_samples(state: TraceState, scene: DeviceScene, bvh=None, lights=None, 
 def trace_sample_range(state: TraceState, scene: DeviceScene, params: Params, begin: int, end: int) -> None:
     """The sharding unit: samples [begin, end) of every pixel."""
     jp = to_jt_params(params, state.jp.accumulate)
-    _lib.check(state.L.jt_trace_sample_range(scene.h, state.h, C.byref(jp), begin, end))
+    if isinstance(state, GroupState):
+        _lib.check(state.L.jt_group_trace_sample_range(scene.h, state.h, C.byref(jp), begin, end))
+    else:
+        _lib.check(state.L.jt_trace_sample_range(scene.h, state.h, C.byref(jp), begin, end))
 
 
 def get_image(state: TraceState) -> np.ndarray:

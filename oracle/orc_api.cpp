@@ -287,6 +287,33 @@ ORC_API void orc_trace_pixel(void* h, const jt_params* p, int32_t i, int32_t j, 
   radiance_hit[4] = (float)rng.draw;
 }
 
+// The closest-hit queries of one (pixel, sample) path in call order: rays (jt_ray layout) and, per ray, the probed
+// instance (1-based) or -1 for a scene query. Returns the number of queries (at most `max` are written).
+ORC_API int64_t orc_trace_pixel_rays(void* h, const jt_params* p, int32_t i, int32_t j, int32_t sample, jt_ray* rays,
+                                     int64_t* instances, int64_t max) {
+  Oracle* o = (Oracle*)h;
+  Params q = to_params(p);
+  const Camera& camera = o->scene.cameras[q.camera - 1];
+  int64_t idx = o->state.width * j + i;
+  Rng rng{jt_rng_key(q.seed, (uint32_t)idx, (uint32_t)sample), 0};
+  V2 puv = rng.next2();
+  V2 luv = rng.next2();
+  Ray ray = sample_camera(camera, i, j, o->state.width, o->state.height, puv, luv, q.tentfilter);
+  std::vector<Counters::LoggedRay> log;
+  Counters cnt;
+  cnt.log = &log;
+  if (q.sampler == 1) trace_path(o->scene, ray, q, rng, &cnt);
+  else trace_naive(o->scene, ray, q, rng, &cnt);
+  for (int64_t k = 0; k < (int64_t)log.size() && k < max; k++) {
+    const Ray& r = log[(size_t)k].ray;
+    rays[k].o[0] = r.o.x; rays[k].o[1] = r.o.y; rays[k].o[2] = r.o.z;
+    rays[k].d[0] = r.d.x; rays[k].d[1] = r.d.y; rays[k].d[2] = r.d.z;
+    rays[k].tmin = r.tmin; rays[k].tmax = r.tmax;
+    instances[k] = log[(size_t)k].instance;
+  }
+  return (int64_t)log.size();
+}
+
 ORC_API void orc_get_state(void* h, float* image, float* albedo, float* normal, int64_t* hits, int32_t* samples) {
   Oracle* o = (Oracle*)h;
   const State& st = o->state;

@@ -86,6 +86,9 @@ struct Counters {
   uint64_t tlas_nodes = 0, blas_nodes = 0, instance_visits = 0, tri_tests = 0, quad_tests = 0;
   // the share of the above spent inside intersect_instance_bvh (light-pdf probes)
   uint64_t probe_blas_nodes = 0, probe_tri_tests = 0, probe_quad_tests = 0;
+  // optional log of every closest-hit query in call order (orc_trace_pixel_rays: divergence hunting in the tests)
+  struct LoggedRay { Ray ray; int64_t instance; };  // instance = -1: intersect_scene_bvh, else intersect_instance_bvh
+  std::vector<LoggedRay>* log = nullptr;
   void add(const Counters& o) {
     scene_rays += o.scene_rays; light_rays += o.light_rays; camera_paths += o.camera_paths;
     tlas_nodes += o.tlas_nodes; blas_nodes += o.blas_nodes; instance_visits += o.instance_visits;
@@ -318,6 +321,7 @@ inline ShapeIsec intersect_shape_bvh(const Shape& shape, Ray ray, bool find_any,
 inline SceneIsec intersect_scene_bvh(const Scene& scene, Ray ray, bool find_any, Counters* cnt) {
   const BvhTree& bvh = scene.bvh;
   if (cnt) cnt->scene_rays++;
+  if (cnt && cnt->log) cnt->log->push_back(Counters::LoggedRay{ray, -1});
   if (bvh.nodes.empty()) return no_scene_isec();  // the reference throws here
   int64_t stack[256];
   int node_cur = 0;
@@ -358,6 +362,7 @@ inline SceneIsec intersect_instance_bvh(const Scene& scene, int64_t instance_, R
                                         bool find_any, Counters* cnt) {
   const Instance& inst = scene.instances[instance_ - 1];
   if (cnt) { cnt->light_rays++; cnt->instance_visits++; }
+  if (cnt && cnt->log) cnt->log->push_back(Counters::LoggedRay{ray, instance_});
   Ray inv_ray = transform_ray(inverse(inst.frame, true), ray);
   uint64_t n0 = cnt ? cnt->blas_nodes : 0, t0 = cnt ? cnt->tri_tests : 0, q0 = cnt ? cnt->quad_tests : 0;
   ShapeIsec s = intersect_shape_bvh(scene.shapes[inst.shape - 1], inv_ray, find_any, cnt);

@@ -11,17 +11,22 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
+    # build BEFORE the device probe below: on a fresh checkout the probe would otherwise fail to load the library,
+    # every gpu test would be skipped and `pytest -m gpu` would exit 0 without having run a single parity test
+    import __graft_entry__ as g
+    g.build()
 
 
 def pytest_collection_modifyitems(config, items):
-    # -m gpu tests need the device; skip them cleanly (not fail) if someone runs the whole suite on CPU
     import importlib
-    try:
-        n = importlib.import_module("julia-raytracer_b200._lib").lib().jt_device_count()
-    except Exception:
-        n = 0
+    n = importlib.import_module("julia-raytracer_b200._lib").lib().jt_device_count()
     if n > 0:
         return
+    # `-m gpu` asked for explicitly on a machine without a device is an error, not a green run of zero tests
+    markexpr = (config.getoption("-m") or "").strip()
+    if markexpr == "gpu":
+        raise pytest.UsageError("-m gpu selected but libjtrace_b200 sees no CUDA device (there is no CPU fallback)")
+    # the whole suite on a CPU box: gpu tests are skipped, everything else runs
     skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
         if "gpu" in item.keywords:

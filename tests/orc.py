@@ -52,6 +52,9 @@ def lib():
         L.orc_trace_range.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int]
         L.orc_trace_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_trace_pixel.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.orc_trace_pixel_rays.restype = C.c_int64
+        L.orc_trace_pixel_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                           C.c_void_p, C.c_int64]
         L.orc_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.orc_get_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_bsdf_eval.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_void_p]
@@ -152,6 +155,16 @@ class Oracle:
         out = np.zeros(5, np.float32)
         self.L.orc_trace_pixel(self.h, C.byref(params), i, j, sample, out.ctypes.data)
         return out
+
+    def trace_pixel_rays(self, params, i, j, sample, max_rays=4096):
+        """(rays, instances): every closest-hit query of one (pixel, sample) path, in call order; instances[k] is the
+        probed instance (1-based, intersect_instance_bvh) or -1 for a scene query."""
+        rays = np.zeros(max_rays, A.RAY_DTYPE)
+        inst = np.zeros(max_rays, np.int64)
+        n = self.L.orc_trace_pixel_rays(self.h, C.byref(params), i, j, sample, rays.ctypes.data, inst.ctypes.data,
+                                        max_rays)
+        n = min(int(n), max_rays)
+        return rays[:n], inst[:n]
 
     def get_state(self):
         n = self.width * self.height

@@ -161,3 +161,106 @@ def test_format_seconds():
     j = importlib.import_module("julia-raytracer_b200.jtrace")
     assert j.format_seconds(1.5) == "01.500" and j.format_seconds(75.25) == "01:15.250"
     assert j.format_seconds(3700.0) == "01:01:40.000"
+
+
+def _header_prototypes():
+    """name -> number of parameters, parsed from include/jtrace_b200.h."""
+    import re
+    hdr = open(os.path.join(orc.ROOT, "include", "jtrace_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"JT_API\s+[\w\s\*]+?\b(jt_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return protos
+
+
+def _split_top_level(text):
+    """Split on commas that are not nested inside (), [] or {}."""
+    out, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def _julia_ccalls(src):
+    """[(symbol, n_argtypes, n_args)] for every ccall((:sym, LIB), ret, (argtypes...), args...) in a Julia source."""
+    import re
+    out = []
+    for m in re.finditer(r"ccall\(\(:(\w+),\s*LIB\)", src):
+        i, depth = m.start() + len("ccall"), 0
+        j = i
+        while True:  # matching parenthesis of the ccall
+            if src[j] == "(":
+                depth += 1
+            elif src[j] == ")":
+                depth -= 1
+                if depth == 0:
+                    break
+            j += 1
+        parts = _split_top_level(src[i + 1:j])
+        assert len(parts) >= 3 and parts[2].startswith("("), (m.group(1), parts)
+        inner = parts[2][1:-1].strip()
+        types = [t for t in _split_top_level(inner) if t]
+        out.append((m.group(1), len(types), len(parts) - 3))
+    return out
+
+
+def test_julia_glue_matches_the_header():
+    """The Julia binding cannot run here (no julia in the image): check it at the text level instead. Every ccall
+    names a symbol the header declares, passes as many argument types as the C prototype has parameters, and as many
+    values as types; the reference-facing surface INTEGRATION.md documents exists with those signatures."""
+    import re
+    protos = _header_prototypes()
+    src = open(os.path.join(orc.ROOT, "julia-raytracer_b200", "julia", "JtraceB200.jl")).read()
+    calls = _julia_ccalls(src)
+    assert len(calls) >= 12
+    for sym, ntypes, nargs in calls:
+        assert sym in protos, f"ccall of undeclared symbol {sym}"
+        assert ntypes == protos[sym], f"{sym}: {ntypes} argument types, C prototype has {protos[sym]}"
+        assert nargs == ntypes, f"{sym}: {nargs} values for {ntypes} types"
+    used = {c[0] for c in calls}
+    assert {"jt_scene_create", "jt_state_create", "jt_trace_samples", "jt_state_download", "jt_group_create",
+            "jt_group_state_create", "jt_group_trace_samples", "jt_group_state_download", "jt_last_error"} <= used
+    # JtParams mirrors jt_params field for field (names and order)
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(orc.ROOT, "include", "jtrace_b200.h")).read(), flags=re.S)
+    body = re.search(r"typedef struct \{([^}]*)\} jt_params;", hdr, flags=re.S).group(1)
+    c_fields = [f for f in re.findall(r"\b(?:int32_t|uint64_t)\s+(\w+)", body)]
+    jl = re.search(r"struct JtParams\n(.*?)\nend", src, flags=re.S).group(1)
+    jl_fields = re.findall(r"(\w+)::(?:Int32|UInt64)", jl)
+    assert jl_fields[:len(c_fields) - 1] == c_fields[:-1] and len(jl_fields) == len(c_fields) - 1 + 6  # _reserved[6]
+    # the surface INTEGRATION.md's diff relies on
+    assert "import ..Trace: trace_samples" in src
+    assert re.search(r"function trace_samples\(state::TraceState, g::GpuScene, bvh, lights, params::Params", src)
+    assert re.search(r"function gpu_scene\(scene::SceneData, bvh::SceneBvh, lights::TraceLights, state::TraceState, params::Params", src)
+    integ = open(os.path.join(orc.ROOT, "INTEGRATION.md")).read()
+    assert "gpu_scene(scene, bvh, lights, state, params" in integ and "gscene," in integ
+
+
+def test_header_structs_match_ctypes_mirror():
+    """sizeof of every POD struct in the header, compiled by gcc, equals the ctypes mirror's."""
+    import tempfile
+    A = orc.A
+    names = ["jt_frame", "jt_bvh_node", "jt_bvh_desc", "jt_instance", "jt_material", "jt_environment", "jt_camera",
+             "jt_texture_desc", "jt_shape_desc", "jt_light_desc", "jt_scene_desc", "jt_params", "jt_ray", "jt_hit",
+             "jt_counters", "jt_scene_stats", "jt_group_stats"]
+    prog = '#include "jtrace_b200.h"\n#include <stdio.h>\nint main(void){' + "".join(
+        f'printf("%zu\\n", sizeof({n}));' for n in names) + "return 0;}"
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "s.c")
+        open(src, "w").write(prog)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(orc.ROOT, "include"), src, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    for n, s in zip(names, sizes):
+        assert C.sizeof(getattr(A, n)) == s, (n, s, C.sizeof(getattr(A, n)))
