@@ -295,6 +295,12 @@ JT_API int jt_group_state_download(jt_group_state* state, float* image_rgba, flo
                                    int64_t* hits);
 JT_API int jt_group_state_download_srgb8(jt_group_state* state, uint8_t* rgba8);
 
+/* ---- diagnostics ------------------------------------------------------------------------------------------------ */
+/* Read bandwidth of a `bytes`-sized device buffer streamed `reps` times by one resident wave of 128-bit loads (best of
+ * 5 launches, CUDA events), in GB/s. With bytes well below the L2 size this is the L2 roofline denominator SURVEY.md 8d
+ * asks for; with bytes >> L2 it reproduces the HBM read peak. */
+JT_API int jt_probe_read_bandwidth(int device, int64_t bytes, int reps, float* gbs_out);
+
 /* ---- host-side helpers (CPU code; the steps bvh.jl performs on the Julia host) --------------- */
 /* make_bvh (src/bvh.jl:138-183) with split_middle (:185-216) or split_sah (:218-274):
  * bboxes = n x {min[3], max[3]} floats. nodes_out must hold 2*n+1 entries, primitives_out n. */

@@ -23,7 +23,7 @@ EXPORTS = [
     "jt_group_create", "jt_group_destroy", "jt_group_get_stats", "jt_group_scene", "jt_group_counters",
     "jt_group_state_create", "jt_group_state_destroy", "jt_group_state_size", "jt_group_state_reset",
     "jt_group_trace_samples", "jt_group_trace_sample_range", "jt_group_synchronize",
-    "jt_group_state_download", "jt_group_state_download_srgb8",
+    "jt_group_state_download", "jt_group_state_download_srgb8", "jt_probe_read_bandwidth",
 ]
 
 
@@ -73,6 +73,7 @@ def lib() -> C.CDLL:
     L.jt_sample_camera.argtypes = [vp, C.POINTER(A.jt_params), i32, i32, vp, vp, i64, vp]
     L.jt_intersect_device.argtypes = [vp, vp, i64, C.c_int, vp]
     L.jt_make_bvh.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
+    L.jt_probe_read_bandwidth.argtypes = [C.c_int, i64, C.c_int, f32p]
     L.jt_group_create.argtypes = [vp, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
     L.jt_group_destroy.argtypes = [vp]
     L.jt_group_destroy.restype = None

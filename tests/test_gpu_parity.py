@@ -34,6 +34,48 @@ def pair(scenes):
         d.close()
 
 
+# Wide-BVH mode vs the oracle on a fixed sample set: the only admissible source of a differing pixel is the residual
+# class of DESIGN.md section 1 (the reference's non-conservative slab test culls a node that holds the true closest hit;
+# the wide BVH's conservative boxes keep it). Measured on B200 (profiles/r02/pytest_gpu_*.log): the fraction of pixels
+# differing by > 1e-4 is 0 on every small case and <= 3e-6 at the BASELINE sizes; the bound is that plus a margin
+# for other sample sets, NOT the 2e-3 of round 1.
+WIDE_PIXEL_FRACTION_BOUND = 5e-5
+
+
+def wide_mode_check(tag, o, d, op, img, ref_img, spp, sample_begin=0):
+    """Print the measured fraction of pixels differing by more than 1e-4 (north-star gate 2), bound it, and EXPLAIN
+    every differing pixel: replay the oracle's rays of that pixel's samples through both GPU traversals; the first
+    closest-hit query on which the wide traversal departs from the reference must return a strictly closer hit."""
+    err = np.abs(img - ref_img).max(axis=-1)
+    bad = err > 1e-4
+    frac = float(bad.mean())
+    print(f"\n[{tag}] wide traversal vs oracle: {int(bad.sum())} of {bad.size} pixels differ by > 1e-4 "
+          f"(fraction {frac:.2e}, max |diff| {float(err.max()):.3g})")
+    assert frac <= WIDE_PIXEL_FRACTION_BOUND, frac
+    h, w = bad.shape
+    for j, i in np.argwhere(bad)[:64]:
+        explained = False
+        for s_ in range(sample_begin, sample_begin + spp):
+            rays, inst = o.trace_pixel_rays(op, int(i), int(j), s_)
+            scene_q = inst < 0
+            got = np.zeros(len(rays), orc.A.HIT_DTYPE)
+            want = np.zeros(len(rays), orc.A.HIT_DTYPE)
+            if scene_q.any():
+                got[scene_q] = d.intersect(rays[scene_q], 0)
+                want[scene_q] = o.intersect(rays[scene_q])
+            if (~scene_q).any():
+                got[~scene_q] = d.intersect_instance(rays[~scene_q], inst[~scene_q], 0)
+                want[~scene_q] = o.intersect_instance(rays[~scene_q], inst[~scene_q])
+            differs = (got["instance"] != want["instance"]) | (got["element"] != want["element"]) | (got["hit"] != want["hit"])
+            if differs.any():
+                k = int(np.argmax(differs))  # the path is only comparable up to its first divergent query
+                closer = got["hit"][k] == 1 and (want["hit"][k] == 0 or got["distance"][k] < want["distance"][k])
+                assert closer, (tag, int(i), int(j), s_, k, got[k], want[k])
+                explained = True
+        assert explained, f"{tag}: pixel ({i}, {j}) differs but none of its rays is in the residual class"
+    return frac
+
+
 def _params(**kw):
     d = dict(scene="x", resolution=64, samples=3, batch=3, sampler=1, camera=1)
     d.update(kw)
@@ -121,8 +163,10 @@ def test_fixed_sample_set_images(pair, name, sampler, extra):
             assert np.array_equal(st.normal.reshape(h, w, 3), ref["normal"])
             assert np.array_equal(st.hits.reshape(h, w), ref["hits"])
             assert (c["camera_paths"], c["scene_rays"], c["light_rays"]) == (oc["camera_paths"], oc["scene_rays"], oc["light_rays"])
+        elif integrator == "wavefront":
+            wide_mode_check(f"{name} sampler {sampler} {res}px", o, d, op, img, ref["image"], 3)
         else:
-            assert (err > 1e-4).mean() <= 2e-3, (err > 1e-4).mean()
+            assert (err > 1e-4).mean() <= WIDE_PIXEL_FRACTION_BOUND, (err > 1e-4).mean()
         st.close()
 
 
@@ -275,7 +319,7 @@ def test_baseline_config_c1_full_size_is_bit_exact(pair):
             assert np.array_equal(st.albedo.reshape(h, w, 3), ref["albedo"])
             assert np.array_equal(st.normal.reshape(h, w, 3), ref["normal"])
         else:
-            assert (np.abs(img - ref["image"]).max(axis=-1) > 1e-4).mean() <= 2e-3
+            wide_mode_check("C1 cornellbox naive 720px 16spp", o, d, op, img, ref["image"], 16)
         st.close()
 
 
@@ -309,7 +353,8 @@ def test_baseline_configs_full_size_properties(pair, name, res, size):
     img, hits = imgs["wide"]
     assert np.isfinite(img).all()
     differing = np.abs(img - imgs["reference"][0]).max(axis=-1) > 1e-4
-    assert differing.mean() <= 2e-3, differing.mean()
+    print(f"\n[{name} {size[0]}x{size[1]} {spp}spp] GPU wide vs GPU reference-order: fraction of differing pixels {differing.mean():.2e}")
+    assert differing.mean() <= WIDE_PIXEL_FRACTION_BOUND, differing.mean()
     assert hits.max() <= spp and np.allclose(img[:, 3], hits / np.float32(spp), atol=1e-6)
     again = trace.make_trace_state(d, p)
     trace.trace_sample_range(again, d, p, 0, 1)  # different chunking, same samples
@@ -333,6 +378,160 @@ def test_baseline_configs_full_size_properties(pair, name, res, size):
     whole.close()
 
 
+@pytest.mark.parametrize("name,res,size", FULL_SIZE)
+def test_baseline_configs_full_size_against_the_oracle(pair, name, res, size):
+    """BASELINE configs C2-C5 at their full image sizes, path sampler, 2 spp, ORACLE vs GPU (not GPU vs GPU):
+    * reference-order traversal + wavefront integrator: image, albedo, normal, hits and the ray counters bit-exact;
+    * the BENCHMARKED mode (wide traversal + wavefront): measured fraction of differing pixels printed and bounded,
+      every differing pixel traced back to a residual-class ray."""
+    o, d = pair(name)
+    spp = 2
+    op = orc.make_params(resolution=res, samples=spp, batch=spp, sampler=1, seed=0)
+    w, h = o.make_state(op)
+    assert (w, h) == size
+    o.counters(reset=True)
+    o.trace_samples(op)
+    ref = o.get_state()
+    oc = o.counters(reset=True)
+    for traversal in ("reference", "wide"):
+        p = _params(scene=name, resolution=res, samples=spp, batch=spp, sampler=1, gpu_traversal=traversal)
+        st = trace.make_trace_state(d, p)
+        d.counters(reset=True)
+        trace.trace_samples(st, d, None, None, p)
+        st.sync()
+        c = d.counters()
+        img = st.image.reshape(h, w, 4)
+        if traversal == "reference":
+            assert np.array_equal(img, ref["image"]), float(np.abs(img - ref["image"]).max())
+            assert np.array_equal(st.albedo.reshape(h, w, 3), ref["albedo"])
+            assert np.array_equal(st.normal.reshape(h, w, 3), ref["normal"])
+            assert np.array_equal(st.hits.reshape(h, w), ref["hits"])
+            assert (c["camera_paths"], c["scene_rays"], c["light_rays"]) == (oc["camera_paths"], oc["scene_rays"], oc["light_rays"])
+        else:
+            assert c["camera_paths"] == oc["camera_paths"]
+            wide_mode_check(f"{name} {w}x{h} path {spp}spp (BASELINE size)", o, d, op, img, ref["image"], spp)
+        st.close()
+
+
+def test_ecosys_converged_render_masked(pair):
+    """North-star gate 3 for C5: the reference's shipped ecosys render (1280x640) against the GPU render at the same
+    size. The checkout lacks shape002/003.ply (the three trees, 8 instances), so the trees and the middle tree's
+    reflection are masked out (test_oracle.ECOSYS_TREE_RECTS); the sky (directly visible environment: also the pin of
+    the HDR loader rule) and the plant-covered ground are gated separately."""
+    import os
+    from PIL import Image
+    from test_oracle import ecosys_masks
+    _, d = pair("ecosys")
+    ref8 = np.asarray(Image.open(os.path.join(orc.ROOT, "tests", "golden", "ref_ecosys_path.png")).convert("RGB"), np.float32)
+    spp = 256
+    p = _params(scene="ecosys", resolution=1280, samples=spp, batch=spp, sampler=1)
+    st = trace.make_trace_state(d, p)
+    assert (st.width, st.height) == (1280, 640)
+    trace.trace_samples(st, d, None, None, p)
+    st.sync()
+    lin = st.image.reshape(st.height, st.width, 4)[..., :3]
+    enc = jt.sceneio.image_to_srgb8(np.concatenate([lin, np.ones(lin.shape[:2] + (1,), np.float32)], axis=2))[..., :3]
+    mine = np.asarray(Image.fromarray(enc.astype(np.uint8), "RGB").resize((ref8.shape[1], ref8.shape[0]), Image.BOX), np.float32)
+    keep, sky = ecosys_masks(*ref8.shape[:2])
+    ground = keep & ~sky
+    dd = mine - ref8
+    out = {}
+    for tag, m in (("sky", sky), ("ground", ground)):
+        out[tag] = (abs(mine[m].mean() - ref8[m].mean()), float(np.sqrt((dd[m] ** 2).mean())))
+        print(f"\n[ecosys path {spp} spp, {tag}: {m.mean():.0%} of the image] mean diff {out[tag][0]:.2f}, RMSE {out[tag][1]:.2f} (8-bit units)")
+    st.close()
+    assert out["sky"][0] < 0.6 and out["sky"][1] < 1.5
+    assert out["ground"][0] < 4.0 and out["ground"][1] < 12.0  # plant placement is identical, leaf-level detail is not converged in either
+
+
+# ---- in-library multi-GPU (jt_group) on ONE device: logical shards {0, 0} ---------------------------------------------
+def test_group_logical_shards_match_single_device(scenes):
+    """jt_group with devices = [0, 0, 0]: three members on one GPU render disjoint sample sub-ranges into sum buffers and
+    the fused reduce + finalize kernel merges them. The union is the single-device sample set, so image / albedo /
+    normal agree to float-addition order and hits exactly; the 8-bit path agrees to +-1 LSB; counters add up."""
+    sc, bvh, lights = scenes("features1")
+    g = trace.DeviceGroup(sc, bvh, lights, [0, 0, 0])
+    single = trace.DeviceScene(sc, bvh, lights, 0)
+    try:
+        gs = g.stats()
+        assert gs["members"] == 3 and gs["distinct_devices"] == 1 and gs["peer_members"] == 0 and gs["staged_members"] == 0
+        p = _params(scene="features1", resolution=200, samples=7, batch=1, sampler=1)
+        a = trace.make_trace_state(g, p)
+        assert isinstance(a, trace.GroupState)
+        for _ in range(7):  # the reference's call pattern: samples / batch calls on ONE thread
+            trace.trace_samples(a, g, None, None, p)
+        assert a.samples == 7
+        trace.trace_samples(a, g, None, None, p)  # no-op once samples == params.samples
+        assert a.samples == 7
+        b = trace.make_trace_state(single, p, accumulate=1)
+        trace.trace_sample_range(b, single, p, 0, 7)
+        b.sync()
+        assert (a.width, a.height) == (b.width, b.height)
+        assert np.allclose(a.image, b.image, rtol=2e-6, atol=1e-7)
+        assert np.allclose(a.albedo, b.albedo, rtol=2e-6, atol=1e-7) and np.allclose(a.normal, b.normal, rtol=2e-6, atol=1e-6)
+        assert np.array_equal(a.hits, b.hits)
+        c = g.counters()
+        assert c["camera_paths"] == a.width * a.height * 7 == single.counters()["camera_paths"]
+        assert np.abs(a.srgb8().astype(np.int32) - b.srgb8().astype(np.int32)).max() <= 1
+        # member scenes are reachable for the parity hooks
+        m1 = g.member(1)
+        rays = raygen.camera_rays(orc.Oracle(sc, bvh, lights), orc.make_params(resolution=64), 64, 27, 2000, seed=5)
+        assert m1.intersect(rays, 0).tobytes() == single.intersect(rays, 0).tobytes()
+        # ranges, reset, errors
+        a.reset()
+        assert a.samples == 0
+        trace.trace_sample_range(a, g, p, 0, 3)
+        trace.trace_sample_range(a, g, p, 3, 7)
+        a.sync()
+        assert np.allclose(a.image, b.image, rtol=2e-6, atol=1e-7) and np.array_equal(a.hits, b.hits)
+        bad = trace.to_jt_params(p, 1)
+        bad.bounces = 300  # rejected by every member -> surfaces from the next blocking call
+        assert g.L.jt_group_trace_sample_range(g.h, a.h, C.byref(bad), 7, 8) == 0
+        assert g.L.jt_group_synchronize(g.h) == -1 and b"member" in g.L.jt_last_error()
+    finally:
+        g.close()
+        single.close()
+    with pytest.raises(libmod.JtError):
+        trace.DeviceGroup(sc, bvh, lights, [0, 99])
+
+
+def test_group_main_drop_in(tmp_path):
+    """Jtrace.main --gpu-devices 0,0: the reference's command line, sharded inside the library."""
+    import os
+    j = importlib.import_module("julia-raytracer_b200.jtrace")
+    out = str(tmp_path / "out.png")
+    scene = os.path.join(orc.ROOT, "assets", "scenes", "cornellbox.jtscene")
+    r = j.main(f"--scene {scene} --sampler path --resolution 96 --samples 6 --batch 2 --output {out} --gpu-devices 0,0")
+    assert os.path.exists(out) and r["image"].shape == (96, 96, 4) and r["counters"]["camera_paths"] == 96 * 96 * 6
+    one = j.main(f"--scene {scene} --sampler path --resolution 96 --samples 6 --batch 2 --output {out}")
+    assert np.allclose(r["image"], one["image"], rtol=1e-5, atol=1e-6)
+
+
+def test_state_outlives_scene_and_bounce_limits(scenes):
+    """a state whose scene was destroyed is an orphan (entry points fail cleanly, destroy is safe); the
+    wavefront integrator rejects bounce counts its packed control word cannot hold."""
+    sc, bvh, lights = scenes("cornellbox")
+    d = trace.DeviceScene(sc, bvh, lights, 0)
+    L = d.L
+    jp = trace.to_jt_params(_params())
+    h = C.c_void_p()
+    assert L.jt_state_create(d.h, C.byref(jp), C.byref(h)) == 0
+    jp.bounces = 255
+    h2 = C.c_void_p()
+    assert L.jt_state_create(d.h, C.byref(jp), C.byref(h2)) == -1 and b"bounces" in L.jt_last_error()
+    jp.bounces = -1
+    assert L.jt_state_create(d.h, C.byref(jp), C.byref(h2)) == -1
+    jp.integrator = 1  # the megakernel takes any value (the reference loop simply runs 0 times)
+    assert L.jt_state_create(d.h, C.byref(jp), C.byref(h2)) == 0
+    L.jt_state_destroy(h2)
+    L.jt_scene_destroy(d.h)
+    d.h = None
+    img = np.zeros(64 * 64 * 4, np.float32)
+    assert L.jt_state_download(h, img.ctypes.data, None, None, None) == -1 and b"destroyed" in L.jt_last_error()
+    assert L.jt_state_reset(h) == -1
+    L.jt_state_destroy(h)  # no use-after-free
+
+
 @pytest.mark.parametrize("res", [33, 50, 301])
 def test_odd_image_sizes_are_bit_exact(pair, res):
     """Slot counts that are not multiples of 16 / 32 / the pipeline split (the flag compaction's scalar tail, padded shade
@@ -353,5 +552,5 @@ def test_odd_image_sizes_are_bit_exact(pair, res):
             if traversal == "reference":
                 assert np.array_equal(img, ref["image"]) and np.array_equal(st.hits.reshape(h, w), ref["hits"])
             else:
-                assert (np.abs(img - ref["image"]).max(axis=-1) > 1e-4).mean() <= 2e-3
+                wide_mode_check(f"cornellbox {res}px sampler {sampler}", o, d, op, img, ref["image"], 3)
             st.close()
