@@ -316,7 +316,13 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK) k_intersect_persist(JtDevSce
                                                                         int* fetch_counter) {
   const unsigned FULL = 0xFFFFFFFFu;
   const int count = (int)n;
-  uint2 stack[JT_WIDE_STACK];
+  uint2 stack_local[JT_WIDE_STACK - JT_SMEM_STACK];
+  TravStack stack;
+  stack.local = stack_local;
+#if JT_SMEM_STACK > 0 && !defined(JT_EMU_COUNT)
+  __shared__ uint2 stack_shared[JT_SMEM_STACK * JT_PERSIST_BLOCK];
+  stack.shared = stack_shared + threadIdx.x;
+#endif
   PersistLane L;
   bool live = false, more = true;
   int s = -1;
@@ -768,7 +774,7 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
           k_wf_shade<2, MODE><<<gs, JT_SHADE_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
           sc->launches += 3;
         }
-        k_wf_regen<<<(unsigned)((B.n + WF_REGEN_BLOCK * WF_REGEN_PER_THREAD - 1) / (WF_REGEN_BLOCK * WF_REGEN_PER_THREAD)), WF_REGEN_BLOCK, 0, q>>>(B, cur[k]);
+        k_wf_regen<<<(unsigned)((B.n + WF_REGEN_BLOCK * WF_REGEN_PER_THREAD - 1) / (WF_REGEN_BLOCK * WF_REGEN_PER_THREAD)), WF_REGEN_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, cur[k], end);
         cur[k] = next;
       }
       st->wf_iterations++;

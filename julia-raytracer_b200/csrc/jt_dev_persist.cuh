@@ -21,6 +21,38 @@
 #define JT_PERSIST_BLOCK 384 /* x 2 blocks per SM; 128 x 6: -5 %, 256 x 3: -1 %, 768 x 1: -1 % (tuning_variants.txt) */
 #endif
 
+// Traversal stack: entries 0 .. JT_SMEM_STACK-1 live in shared memory (one column per thread, so a warp's accesses to
+// one level are conflict-free 8-byte words), deeper ones in local memory. JT_SMEM_STACK = 0: all local.
+#ifndef JT_SMEM_STACK
+#define JT_SMEM_STACK 0
+#endif
+struct TravStack {
+  uint2* local;
+#if JT_SMEM_STACK > 0 && !defined(JT_EMU_COUNT)
+  uint2* shared;  // this thread's column: element i at shared[i * JT_PERSIST_BLOCK]
+  JT_DEV void put(int i, uint2 v) const {
+    if (i < JT_SMEM_STACK) shared[i * JT_PERSIST_BLOCK] = v;
+    else local[i - JT_SMEM_STACK] = v;
+  }
+  JT_DEV uint2 get(int i) const { return i < JT_SMEM_STACK ? shared[i * JT_PERSIST_BLOCK] : local[i - JT_SMEM_STACK]; }
+#else
+  JT_DEV void put(int i, uint2 v) const { local[i] = v; }
+  JT_DEV uint2 get(int i) const { return local[i]; }
+#endif
+};
+
+// Postponed work is popped several iterations after it was pushed: warm the L1 with its first record meanwhile.
+#ifndef JT_PREFETCH_POSTPONED
+#define JT_PREFETCH_POSTPONED 0
+#endif
+JT_DEV void prefetch_l1(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 struct PersistLane {
   WideRay R;            // current space (world or instance)
   uint2 ngroup, tgroup;
@@ -49,7 +81,7 @@ JT_DEV void persist_init(PersistLane& L, const JtDevScene& S, f3 o, f3 d, float 
 
 // One warp-uniform traversal episode: runs until every lane has finished its ray or (when `more` rays
 // are waiting) fewer than JT_FETCH_THRESHOLD lanes remain live. `live` is updated per lane.
-JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, uint2* stack, bool& live, bool more) {
+JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, const TravStack& stack, bool& live, bool more) {
   const unsigned FULL = 0xFFFFFFFFu;
   for (;;) {
     unsigned am = __ballot_sync(FULL, live);
@@ -62,7 +94,7 @@ JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, uint2* stack, 
         uint32_t bit = 31u - (uint32_t)__clz(hits);
         hits &= ~(1u << bit);
         L.ngroup.y = hits;
-        if (hits > 0x00FFFFFFu) stack[L.sp++] = L.ngroup;
+        if (hits > 0x00FFFFFFu) stack.put(L.sp++, L.ngroup);
         uint32_t slot = (bit - 24u) ^ L.R.oct;
         uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
         wide_node_hits(S.wnodes, L.ngroup.x + rel, L.R, L.tmin, L.best_t, &L.ngroup, &L.tgroup);
@@ -90,8 +122,8 @@ JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, uint2* stack, 
         uint32_t flags = __float_as_uint(r2.w);
         if (flags & 0x100u) {  // instance record: park world-level work, enter the BLAS
           int inst = __float_as_int(r1.w);
-          if (L.tgroup.y != 0u) stack[L.sp++] = L.tgroup;
-          if (L.ngroup.y > 0x00FFFFFFu) stack[L.sp++] = L.ngroup;
+          if (L.tgroup.y != 0u) stack.put(L.sp++, L.tgroup);
+          if (L.ngroup.y > 0x00FFFFFFu) stack.put(L.sp++, L.ngroup);
           L.blas_sp = L.sp;
           L.cur_inst = inst;
           const JtInstanceRec& I = S.instances[inst];
@@ -120,7 +152,14 @@ JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, uint2* stack, 
     // ---- C: postpone leftovers, pop the next group, leave the BLAS, or finish ---------------------------
     if (live) {
       if (L.tgroup.y != 0u) {
-        stack[L.sp++] = L.tgroup;
+        stack.put(L.sp++, L.tgroup);
+#if JT_PREFETCH_POSTPONED
+        {
+          const float4* tp = S.wtris + 3 * (size_t)(L.tgroup.x + (uint32_t)__ffs((int)L.tgroup.y) - 1u);
+          prefetch_l1(tp);
+          prefetch_l1(tp + 2);
+        }
+#endif
         L.tgroup = make_uint2(0u, 0u);
       }
       if (L.ngroup.y <= 0x00FFFFFFu) {
@@ -130,7 +169,7 @@ JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, uint2* stack, 
           wide_ray_setup(L.R, L.wo, L.wd);
         }
         if (L.sp == 0) live = false;
-        else L.ngroup = stack[--L.sp];
+        else L.ngroup = stack.get(--L.sp);
       }
     }
   }

@@ -15,11 +15,11 @@
 //                                                                       -> q_probe | q_extend | regen flag
 //   probe    : sample_lights_pdf (the chained intersect_instance_bvh probes), MIS weight,
 //              Russian roulette                                                   -> q_extend | regen flag
-//   regen    : slots flagged as "new camera ray started in place" join the next extend queue in
-//              slot (= pixel) order; consumed queue counters are recycled
-// A slot that terminates a sample accumulates it (running mean or sum) and regenerates the next
-// sample of ITS pixel in place, so samples of one pixel are still accumulated in order (Q13) with
-// no atomics on the image. Queue appends are warp-aggregated: one atomicAdd per warp per queue,
+//   regen    : slots whose sample ended this iteration (flagged by shade / probe) are visited in slot (= pixel)
+//              order: the sample is accumulated (running mean or sum), the next sample of the same pixel is
+//              started in place and the slot joins the next extend queue; consumed queue counters are recycled
+// A slot holds one sample of ITS pixel at a time, so samples of one pixel are still accumulated in
+// order (Q13) with no atomics on the image. Queue appends are warp-aggregated: one atomicAdd per warp per queue,
 // lane offsets from ballot / match_any masks; the per-slot state is interleaved (WfBuffers).
 #pragma once
 #include "jt_dev_persist.cuh"
@@ -179,6 +179,34 @@ JT_DEV bool wf_finish_sample(const JtDevScene& S, const WfBuffers& B, const DevS
   return false;
 }
 
+// The end of a sample is DEFERRED to k_wf_regen (JT_DEFER_FINISH, default): shade / probe only park the final
+// radiance and the control word and flag the slot. The accumulate (3 read-modify-writes of image buffers), the
+// recomputation of the camera direction for the normal AOV of a miss and the next sample's camera ray are the most
+// divergent tail of the shading kernels (4.9-9.3 of 32 lanes in profiles/r01/hot_lines_shade_v4.txt) and scatter
+// over the image in queue order; in k_wf_regen the same work runs compacted, in pixel order, in full warps.
+#ifndef JT_DEFER_FINISH
+#define JT_DEFER_FINISH 1
+#endif
+#define WF_REGEN_CONTINUE 1 /* sample ended, another one follows for this pixel */
+#define WF_REGEN_LAST 2     /* sample ended, it was the last one of the range */
+JT_DEV void wf_end_sample(const JtDevScene& S, const WfBuffers& B, const DevState& st, const DevParams& P, int s,
+                          const WfPath& p, f3 radiance, int sample_end, unsigned long long* counters) {
+#if JT_DEFER_FINISH
+  B.rad[s] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+  wf_store_ctl(B, s, p);
+  B.regen[s] = ((int)p.sample + 1 < sample_end) ? WF_REGEN_CONTINUE : WF_REGEN_LAST;
+#else
+  if (wf_finish_sample(S, B, st, P, s, p, radiance, sample_end, counters)) B.regen[s] = WF_REGEN_CONTINUE;
+#endif
+}
+// k_wf_regen's per-slot work under JT_DEFER_FINISH: accumulate the parked sample, start the next one.
+JT_DEV void wf_regen_slot(const JtDevScene& S, const WfBuffers& B, const DevState& st, const DevParams& P, int s,
+                          int sample_end) {
+  WfPath p = wf_load_ctl(B, s);
+  float4 r = B.rad[s];
+  wf_finish_sample(S, B, st, P, s, p, f3{r.x, r.y, r.z}, sample_end, nullptr);
+}
+
 // ---- generate ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_wf_generate(JtDevScene S, WfBuffers B, DevParams P, int sample_begin,
                                                      int sample_end, unsigned long long* counters) {
@@ -227,7 +255,13 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
   const unsigned FULL = 0xFFFFFFFFu;
   const int count = B.counts[WF_C_EXT(cur)];
   const int* queue = B.q_ext[cur];
-  uint2 stack[JT_WIDE_STACK];
+  uint2 stack_local[JT_WIDE_STACK - JT_SMEM_STACK];
+  TravStack stack;
+  stack.local = stack_local;
+#if JT_SMEM_STACK > 0 && !defined(JT_EMU_COUNT)
+  __shared__ uint2 stack_shared[JT_SMEM_STACK * JT_PERSIST_BLOCK];
+  stack.shared = stack_shared + threadIdx.x;
+#endif
   PersistLane L;
   bool live = false, more = true;
   int s = -1;
@@ -515,7 +549,7 @@ __global__ void __launch_bounds__(JT_SHADE_BLOCK, JT_SHADE_MINBLOCKS) k_wf_shade
       wf_store_ctl(B, s, p);
     } else {
       to_probe = false;
-      if (wf_finish_sample(S, B, st, P, s, p, radiance, sample_end, counters)) B.regen[s] = 1;  // queued in pixel order by k_wf_regen
+      wf_end_sample(S, B, st, P, s, p, radiance, sample_end, counters);  // accumulated + regenerated in pixel order by k_wf_regen
     }
   }
   wf_append(B.q_probe, B.counts + WF_C_PROBE, to_probe, s);
@@ -550,8 +584,13 @@ __global__ void __launch_bounds__(JT_PROBE_BLOCK, JT_PROBE_MINBLOCKS) k_wf_probe
       wf_store_ctl(B, s, p);
       to_extend = true;
     } else {
+#if JT_DEFER_FINISH
+      // radiance and the control word (sample index, first-hit flag) were parked by the shade kernel
+      B.regen[s] = ((int)p.sample + 1 < sample_end) ? WF_REGEN_CONTINUE : WF_REGEN_LAST;
+#else
       float4 rad4 = B.rad[s];
-      if (wf_finish_sample(S, B, st, P, s, p, f3{rad4.x, rad4.y, rad4.z}, sample_end, counters)) B.regen[s] = 1;
+      if (wf_finish_sample(S, B, st, P, s, p, f3{rad4.x, rad4.y, rad4.z}, sample_end, counters)) B.regen[s] = WF_REGEN_CONTINUE;
+#endif
     }
   }
   wf_append(B.q_ext[next], B.counts + WF_C_EXT(next), to_extend, s);
@@ -560,17 +599,21 @@ __global__ void __launch_bounds__(JT_PROBE_BLOCK, JT_PROBE_MINBLOCKS) k_wf_probe
 }
 
 // ---- regen + advance -------------------------------------------------------------------------------------------
-// Closes an iteration: (1) the slots that started a new camera ray this iteration (flagged by shade / probe) are
-// appended to the next extend queue IN SLOT (= PIXEL) ORDER, chunk by chunk, so that camera rays of neighbouring
-// pixels sit in neighbouring lanes of the extend kernel -- queues built by atomics scatter them among the bounce rays,
-// and the same mix traverses 11 % slower (tools/exp_coherence.py: 2 534 vs 2 827 Mrays/s on classroom);
-// (2) the consumed queues' counters are recycled.
+// Closes an iteration: (1) the slots whose sample ended this iteration (flagged by shade / probe) are compacted IN SLOT
+// (= PIXEL) ORDER, block by block; their sample is accumulated, the next sample of the pixel is started in place and the
+// slot is appended to the next extend queue, so that camera rays of neighbouring pixels sit in neighbouring lanes of the
+// extend kernel -- queues built by atomics scatter them among the bounce rays, and the same mix traverses 11 % slower
+// (tools/exp_coherence.py: 2 534 vs 2 827 Mrays/s on classroom); (2) the consumed queues' counters are recycled.
 #define WF_REGEN_BLOCK 256
 #define WF_REGEN_PER_THREAD 16 /* one 128-bit load of flags */
 #ifndef JT_EMU_COUNT
-__global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(WfBuffers B, int cur) {
-  __shared__ int warp_sums[WF_REGEN_BLOCK / 32];
+__global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(JtDevScene S, WfBuffers B, DevState st, DevParams P, int cur,
+                                                             int sample_end) {
+  __shared__ int warp_sums[2][WF_REGEN_BLOCK / 32];
   __shared__ int block_base;
+#if JT_DEFER_FINISH
+  __shared__ int ended[WF_REGEN_BLOCK * WF_REGEN_PER_THREAD];  // slots of this block whose sample ended, in slot order
+#endif
   const int next = cur ^ 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     B.counts[WF_C_EXT(cur)] = 0;
@@ -579,47 +622,81 @@ __global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(WfBuffers B, int cu
     for (int k = 0; k < WF_NKEY; k++) B.counts[WF_C_SHADEK(k)] = 0;
   }
   const int first = (blockIdx.x * WF_REGEN_BLOCK + threadIdx.x) * WF_REGEN_PER_THREAD;
-  unsigned flags = 0u;  // bit i: slot first + i regenerated
+  unsigned flags = 0u;  // bit i: slot first + i continues with a new camera ray
+  unsigned last = 0u;   // bit i: slot first + i ended its LAST sample (accumulate only)
   if (first + WF_REGEN_PER_THREAD <= B.n) {
     uint4 v = *reinterpret_cast<const uint4*>(B.regen + first);
     unsigned w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; k++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) flags |= ((w[k] >> (8 * j)) & 1u) << (4 * k + j);
-    if (flags) *reinterpret_cast<uint4*>(B.regen + first) = make_uint4(0u, 0u, 0u, 0u);
+      for (int j = 0; j < 4; j++) {
+        flags |= ((w[k] >> (8 * j)) & 1u) << (4 * k + j);
+        last |= ((w[k] >> (8 * j + 1)) & 1u) << (4 * k + j);
+      }
+    if (flags | last) *reinterpret_cast<uint4*>(B.regen + first) = make_uint4(0u, 0u, 0u, 0u);
   } else {
-    for (int i = 0; i < WF_REGEN_PER_THREAD && first + i < B.n; i++)
-      if (B.regen[first + i]) {
-        flags |= 1u << i;
+    for (int i = 0; i < WF_REGEN_PER_THREAD && first + i < B.n; i++) {
+      unsigned char f = B.regen[first + i];
+      if (f) {
+        if (f == WF_REGEN_CONTINUE) flags |= 1u << i;
+        else last |= 1u << i;
         B.regen[first + i] = 0;
       }
+    }
   }
   const int mine = __popc(flags);
-  // block-wide exclusive scan of `mine`
-  int incl = mine;
+  const int mine_all = __popc(flags | last);
+  // block-wide exclusive scans of `mine` (queue positions) and `mine_all` (positions in the ended list)
+  int incl = mine, incl_all = mine_all;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-    if ((int)lane_id() >= d) incl += t;
+    int u = __shfl_up_sync(0xFFFFFFFFu, incl_all, d);
+    if ((int)lane_id() >= d) {
+      incl += t;
+      incl_all += u;
+    }
   }
   const int warp = threadIdx.x >> 5;
-  if (lane_id() == 31u) warp_sums[warp] = incl;
+  if (lane_id() == 31u) {
+    warp_sums[0][warp] = incl;
+    warp_sums[1][warp] = incl_all;
+  }
   __syncthreads();
-  int warp_off = 0, total = 0;
+  int warp_off = 0, total = 0, warp_off_all = 0, total_all = 0;
 #pragma unroll
   for (int k = 0; k < WF_REGEN_BLOCK / 32; k++) {
-    int v = warp_sums[k];
-    if (k < warp) warp_off += v;
+    int v = warp_sums[0][k], u = warp_sums[1][k];
+    if (k < warp) {
+      warp_off += v;
+      warp_off_all += u;
+    }
     total += v;
+    total_all += u;
   }
   if (threadIdx.x == 0) block_base = total ? atomicAdd(B.counts + WF_C_EXT(next), total) : 0;
   __syncthreads();
   int at = block_base + warp_off + incl - mine;
+#if JT_DEFER_FINISH
+  int at_all = warp_off_all + incl_all - mine_all;
+  unsigned both = flags | last;
+  while (both) {
+    int i = __ffs((int)both) - 1;
+    both &= both - 1u;
+    ended[at_all++] = first + i;
+    if (flags & (1u << i)) B.q_ext[next][at++] = first + i;
+  }
+  __syncthreads();
+  // consecutive threads take consecutive ended slots = neighbouring pixels: coalesced accumulator updates, full warps
+  for (int j = threadIdx.x; j < total_all; j += WF_REGEN_BLOCK) wf_regen_slot(S, B, st, P, ended[j], sample_end);
+#else
+  (void)total_all; (void)warp_off_all; (void)last;
   while (flags) {
     int i = __ffs((int)flags) - 1;
     flags &= flags - 1u;
     B.q_ext[next][at++] = first + i;
   }
+#endif
 }
 #endif

@@ -63,7 +63,13 @@ static void put_hit(jt_hit* o, const DHit& h) {
 
 // the persistent-warp traversal state machine (jt_dev_persist.cuh), one single-lane "warp" per ray
 static DHit persist_one(const JtDevScene& S, const DRay& r) {
-  uint2 stack[JT_WIDE_STACK];
+  uint2 stack_local[JT_WIDE_STACK - JT_SMEM_STACK];
+  TravStack stack;
+  stack.local = stack_local;
+#if JT_SMEM_STACK > 0 && !defined(JT_EMU_COUNT)
+  __shared__ uint2 stack_shared[JT_SMEM_STACK * JT_PERSIST_BLOCK];
+  stack.shared = stack_shared + threadIdx.x;
+#endif
   PersistLane L;
   persist_init(L, S, r.o, r.d, r.tmin, r.tmax, S.wide_root, -1);
   bool live = S.wide_root >= 0;
@@ -197,8 +203,12 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
     // k_wf_regen, sequentially: regenerated slots join the next extend queue in slot order; counters recycled
     for (int sl = 0; sl < n; sl++)
       if (regen[sl]) {
+        const bool cont = regen[sl] == WF_REGEN_CONTINUE;
         regen[sl] = 0;
-        q_next_append(B, next, sl);
+#if JT_DEFER_FINISH
+        wf_regen_slot(e->dev, B, st, P, sl, end);  // accumulate the parked sample, start the next one
+#endif
+        if (cont) q_next_append(B, next, sl);
       }
     counts[WF_C_EXT(cur)] = 0; counts[WF_C_PROBE] = 0; counts[WF_C_FETCH] = 0;
     for (int k = 0; k < WF_NKEY; k++) counts[WF_C_SHADEK(k)] = 0;
