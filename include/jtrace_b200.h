@@ -307,6 +307,26 @@ JT_API int jt_probe_read_bandwidth(int device, int64_t bytes, int reps, float* g
 JT_API int jt_make_bvh(const float* bboxes, int64_t n, int high_quality, jt_bvh_node* nodes_out,
                        int64_t* num_nodes_out, int64_t* primitives_out);
 
+/* The whole host side natively (SURVEY.md 8f N2 and the host halves of N1 / N4), for hosts that are not Julia:
+ *   jt_host_scene_load   = load_scene (src/sceneio.jl:25-93): the scene JSON, PLY shapes (src/shape.jl:78-124, quad
+ *                          promotion / fan triangulation :302-446, v-flip), 8-bit PNG and Radiance .hdr textures
+ *                          (src/scene.jl:164-189, with the reference loader's HDR rule) and the missing-asset rule
+ *   jt_host_scene_build  = make_scene_bvh (src/bvh.jl:66-136) + make_trace_lights (src/trace.jl:117-187)
+ *   jt_host_scene_desc   = the flattening pass: a jt_scene_desc over arrays owned by the handle (valid until destroy;
+ *                          BVHs and lights are present after jt_host_scene_build)
+ * Bit-identical to the Python mirror (sceneio.py / bvh.py / lights.py) on every shipped scene: tests/test_native_host.py. */
+typedef struct jt_host_scene jt_host_scene;
+JT_API int jt_host_scene_load(const char* json_path, jt_host_scene** out);
+JT_API int jt_host_scene_build(jt_host_scene* scene, int high_quality_bvh);
+JT_API int jt_host_scene_desc(jt_host_scene* scene, const jt_scene_desc** out);
+/* find_camera (src/scene.jl:358-370): 1-based index of `name`, else of "default" / "camera" / "camera0" / "camera1",
+ * else 1; -1 if the scene has no camera. */
+JT_API int jt_host_scene_find_camera(jt_host_scene* scene, const char* name, int32_t* camera);
+/* Substitutions made by the missing-asset rule (one human-readable line each). */
+JT_API int jt_host_scene_num_notes(jt_host_scene* scene);
+JT_API const char* jt_host_scene_note(jt_host_scene* scene, int index);
+JT_API void jt_host_scene_destroy(jt_host_scene* scene);
+
 #ifdef __cplusplus
 }
 #endif

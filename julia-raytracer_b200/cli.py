@@ -59,6 +59,9 @@ def make_parser() -> argparse.ArgumentParser:
     p.add_argument("--gpu-devices", dest="gpu_devices", type=str, default="",
                    help="comma-separated CUDA device ids (or 'all') to shard the sample axis over, inside one "
                         "process (jt_group: scene replicated, fused peer-to-peer merge); empty = one device")
+    p.add_argument("--gpu-native-host", dest="gpu_native_host", type=_bool, default=False,
+                   help="load the scene, build the BVH and the light CDFs inside the library (jt_host_scene_*) "
+                        "instead of with the Python mirror; same bytes either way")
     return p
 
 
@@ -86,6 +89,7 @@ class Params:  # src/cli.jl:90-108
     gpu_traversal: str = "wide"
     gpu_integrator: str = "wavefront"
     gpu_devices: str = ""
+    gpu_native_host: bool = False
 
     @staticmethod
     def from_args(ns: argparse.Namespace) -> "Params":

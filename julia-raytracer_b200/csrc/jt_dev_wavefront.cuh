@@ -605,7 +605,9 @@ __global__ void __launch_bounds__(JT_PROBE_BLOCK, JT_PROBE_MINBLOCKS) k_wf_probe
 // extend kernel -- queues built by atomics scatter them among the bounce rays, and the same mix traverses 11 % slower
 // (tools/exp_coherence.py: 2 534 vs 2 827 Mrays/s on classroom); (2) the consumed queues' counters are recycled.
 #define WF_REGEN_BLOCK 256
-#define WF_REGEN_PER_THREAD 16 /* one 128-bit load of flags */
+#ifndef WF_REGEN_PER_THREAD
+#define WF_REGEN_PER_THREAD 16 /* slots per thread: one 128-bit (16) or one 32-bit (4) load of flags */
+#endif
 #ifndef JT_EMU_COUNT
 __global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(JtDevScene S, WfBuffers B, DevState st, DevParams P, int cur,
                                                              int sample_end) {
@@ -624,17 +626,28 @@ __global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(JtDevScene S, WfBuf
   const int first = (blockIdx.x * WF_REGEN_BLOCK + threadIdx.x) * WF_REGEN_PER_THREAD;
   unsigned flags = 0u;  // bit i: slot first + i continues with a new camera ray
   unsigned last = 0u;   // bit i: slot first + i ended its LAST sample (accumulate only)
+  static_assert(WF_REGEN_PER_THREAD == 16 || WF_REGEN_PER_THREAD == 4, "flag bytes are read with one 128- or 32-bit load");
   if (first + WF_REGEN_PER_THREAD <= B.n) {
+#if WF_REGEN_PER_THREAD == 16
     uint4 v = *reinterpret_cast<const uint4*>(B.regen + first);
     unsigned w[4] = {v.x, v.y, v.z, v.w};
+#else
+    unsigned w[1] = {*reinterpret_cast<const unsigned*>(B.regen + first)};
+#endif
 #pragma unroll
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < WF_REGEN_PER_THREAD / 4; k++)
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         flags |= ((w[k] >> (8 * j)) & 1u) << (4 * k + j);
         last |= ((w[k] >> (8 * j + 1)) & 1u) << (4 * k + j);
       }
-    if (flags | last) *reinterpret_cast<uint4*>(B.regen + first) = make_uint4(0u, 0u, 0u, 0u);
+    if (flags | last) {
+#if WF_REGEN_PER_THREAD == 16
+      *reinterpret_cast<uint4*>(B.regen + first) = make_uint4(0u, 0u, 0u, 0u);
+#else
+      *reinterpret_cast<unsigned*>(B.regen + first) = 0u;
+#endif
+    }
   } else {
     for (int i = 0; i < WF_REGEN_PER_THREAD && first + i < B.n; i++) {
       unsigned char f = B.regen[first + i];

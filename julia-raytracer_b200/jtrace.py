@@ -14,7 +14,7 @@ from .lights import make_trace_lights
 from .scene import find_camera
 from .sceneio import load_scene, save_image, save_srgb8  # noqa: F401
 from . import _lib
-from .trace import DeviceGroup, DeviceScene, get_image, make_trace_state, trace_samples
+from .trace import DeviceGroup, DeviceScene, NativeHostScene, get_image, make_trace_state, trace_samples
 
 
 def format_seconds(seconds: float) -> str:
@@ -60,18 +60,28 @@ def main(params: Union[str, Params, None], device: int = 0, devices=None) -> Opt
     render_start = time.time()
     print(f"loading scene {params.scene}...")
     t0 = time.time()
-    scene = load_scene(params.scene, params.noparallel, verbose=True)
-    print(f"loaded scene in {format_seconds(time.time() - t0)}")
-    for note in scene.notes:
-        print(f"    note: {note}")
-    print("finding camera...")
-    params.camera = find_camera(scene, params.camera if isinstance(params.camera, str) else "")
-    print("building bvh...")
-    t0 = time.time()
-    bvh = make_scene_bvh(scene, params.highqualitybvh, params.noparallel)
-    print(f"built bvh in {format_seconds(time.time() - t0)}")
-    print("making lights...")
-    lights = make_trace_lights(scene, params)
+    native = bool(getattr(params, "gpu_native_host", False)) and not str(params.scene).endswith(".jtscene")
+    if native:  # load_scene + make_scene_bvh + make_trace_lights inside the library (jt_host_scene_*)
+        scene = NativeHostScene(params.scene, params.highqualitybvh)
+        bvh = lights = None
+        print(f"loaded scene, built bvh, made lights (native host) in {format_seconds(time.time() - t0)}")
+        for note in scene.notes:
+            print(f"    note: {note}")
+        print("finding camera...")
+        params.camera = scene.find_camera(params.camera if isinstance(params.camera, str) else "")
+    else:
+        scene = load_scene(params.scene, params.noparallel, verbose=True)
+        print(f"loaded scene in {format_seconds(time.time() - t0)}")
+        for note in scene.notes:
+            print(f"    note: {note}")
+        print("finding camera...")
+        params.camera = find_camera(scene, params.camera if isinstance(params.camera, str) else "")
+        print("building bvh...")
+        t0 = time.time()
+        bvh = make_scene_bvh(scene, params.highqualitybvh, params.noparallel)
+        print(f"built bvh in {format_seconds(time.time() - t0)}")
+        print("making lights...")
+        lights = make_trace_lights(scene, params)
     print("uploading scene to the GPU...")
     t0 = time.time()
     devs = parse_devices(devices if devices is not None else getattr(params, "gpu_devices", ""))

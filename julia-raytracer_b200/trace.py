@@ -39,12 +39,53 @@ def _counters_dict(c: A.jt_counters) -> dict:
                 extend_us=int(c.extend_kernel_us), extend_launches=int(c.extend_launches))
 
 
+class NativeHostScene:
+    """load_scene + make_scene_bvh + make_trace_lights done inside the library (jt_host_scene_*, SURVEY.md 8f N2 and
+    the host halves of N1 / N4): what a C or C++ host uses instead of sceneio.py / bvh.py / lights.py. The arrays are
+    byte-identical to the Python mirror's (tests/test_native_host.py). Pass it to DeviceScene / DeviceGroup in place
+    of `scene` (with bvh = lights = None)."""
+
+    def __init__(self, filename: str, high_quality_bvh: bool = False):
+        self.L = _lib.lib()
+        self.h = C.c_void_p()
+        _lib.check(self.L.jt_host_scene_load(str(filename).encode(), C.byref(self.h)))
+        _lib.check(self.L.jt_host_scene_build(self.h, int(bool(high_quality_bvh))))
+        d = C.POINTER(A.jt_scene_desc)()
+        _lib.check(self.L.jt_host_scene_desc(self.h, C.byref(d)))
+        self.desc = d.contents
+        self.notes = [self.L.jt_host_scene_note(self.h, i).decode()
+                      for i in range(self.L.jt_host_scene_num_notes(self.h))]
+
+    def byref(self):
+        return C.byref(self.desc)
+
+    def find_camera(self, name: str = "") -> int:
+        c = C.c_int32()
+        _lib.check(self.L.jt_host_scene_find_camera(self.h, str(name).encode(), C.byref(c)))
+        return c.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.jt_host_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _flat(scene, bvh, lights):
+    return scene if isinstance(scene, NativeHostScene) else FlatScene(scene, bvh, lights)
+
+
 class DeviceScene:
     """(scene, bvh, lights) resident on one GPU: what `trace_samples` consumes."""
 
-    def __init__(self, scene: SceneData, bvh: SceneBvh, lights: List[TraceLight], device: int = 0):
+    def __init__(self, scene: SceneData, bvh: SceneBvh = None, lights: List[TraceLight] = None, device: int = 0):
         self.L = _lib.lib()
-        self.flat = FlatScene(scene, bvh, lights)
+        self.flat = _flat(scene, bvh, lights)
         h = C.c_void_p()
         _lib.check(self.L.jt_scene_create(self.flat.byref(), device, C.byref(h)))
         self.h = h
@@ -192,7 +233,7 @@ class DeviceGroup:
 
     def __init__(self, scene: SceneData, bvh: SceneBvh, lights: List[TraceLight], devices):
         self.L = _lib.lib()
-        self.flat = FlatScene(scene, bvh, lights)
+        self.flat = _flat(scene, bvh, lights)
         self.devices = [int(d) for d in devices]
         arr = (C.c_int * len(self.devices))(*self.devices)
         h = C.c_void_p()

@@ -15,7 +15,7 @@ build_one() {
     nvcc $NVFLAGS $flags -I$SRC -c $SRC/$f.cu -o $d/$f.o
   done
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/variants/$name.so $d/jt_api.o $d/jt_group.o $d/jt_probe.o \
-     $SRC/jt_host_bvh.o $SRC/jt_wide_bvh.o $SRC/jt_stage.o -cudart static -ccbin /usr/bin/g++ -Xcompiler -fopenmp,-pthread
+     $SRC/jt_host_bvh.o $SRC/jt_wide_bvh.o $SRC/jt_stage.o $SRC/jt_host_scene.o -lz -cudart static -ccbin /usr/bin/g++ -Xcompiler -fopenmp,-pthread
   rm -rf $d
   echo "built variants/$name.so  [$flags]"
 }
