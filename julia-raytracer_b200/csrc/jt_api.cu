@@ -2,6 +2,7 @@
 // TraceState, the render-loop launches and the parity hooks. Kernels live at the bottom.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -695,7 +696,9 @@ static int wf_prepare(jt_scene* sc, jt_state* st) {
     float4 *ga = nullptr, *gb = nullptr, *gc = nullptr, *gd = nullptr;
     if ((rc = alloc((void**)&ga, n * 64)) || (rc = alloc((void**)&gb, n * 64)) || (rc = alloc((void**)&gc, n * 32)) ||
         (rc = alloc((void**)&gd, n * 32)) ||
+        (rc = alloc((void**)&B.parked, n * JT_SUSPEND_STACK * sizeof(uint2))) ||
         (rc = alloc((void**)&B.q_ext[0], n * 4)) || (rc = alloc((void**)&B.q_ext[1], n * 4)) ||
+        (rc = alloc((void**)&B.next_sample, n * 4)) || (rc = alloc((void**)&B.commit, n * 4)) ||
         (rc = alloc((void**)&B.regen, ((n + 15) & ~(size_t)15) + 16)) ||
         (rc = alloc((void**)&B.q_shade, n * 4 * WF_NKEY)) || (rc = alloc((void**)&B.q_probe, n * 4)) ||
         (rc = alloc((void**)&B.counts, WF_C_TOTAL * 4)))
@@ -739,6 +742,8 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
     remaining[k] = B.n;
     active[k] = true;
   }
+  FILE* iter_log = getenv("JT_ITER_LOG") ? fopen(getenv("JT_ITER_LOG"), "a") : nullptr;
+  const auto iter_t0 = std::chrono::steady_clock::now();
   const int pdiv = getenv("JT_PGRID_DIV") ? atoi(getenv("JT_PGRID_DIV")) : 1;
   const unsigned pgrid = std::max(1u, persist_grid(sc) / (unsigned)std::max(1, pdiv));
   // One batch = poll_every iterations of every active pipeline, followed by an async copy of the queue counters.
@@ -752,8 +757,8 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
         WfBuffers& B = st->wf[k];
         cudaStream_t q = st->pipe_stream[k];
         const int next = cur[k] ^ 1;
-        // grids sized from the last polled queue length (an upper bound: queues only shrink, because every slot
-        // appears at most once per iteration)
+        // grids sized from the last polled number of slots that are not idle for good (an upper bound of every queue:
+        // a slot appears at most once per iteration, and idle slots never come back within a range)
         unsigned ge = (unsigned)((remaining[k] + 127) / 128);
         unsigned gs = (unsigned)((remaining[k] + 32 * WF_NKEY + JT_SHADE_BLOCK - 1) / JT_SHADE_BLOCK);
         unsigned gpr = (unsigned)((remaining[k] + JT_PROBE_BLOCK - 1) / JT_PROBE_BLOCK);
@@ -774,7 +779,7 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
           k_wf_shade<2, MODE><<<gs, JT_SHADE_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
           sc->launches += 3;
         }
-        k_wf_regen<<<(unsigned)((B.n + WF_REGEN_BLOCK * WF_REGEN_PER_THREAD - 1) / (WF_REGEN_BLOCK * WF_REGEN_PER_THREAD)), WF_REGEN_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, cur[k], end);
+        k_wf_regen<<<(unsigned)((B.n + WF_REGEN_BLOCK * WF_REGEN_PER_THREAD - 1) / (WF_REGEN_BLOCK * WF_REGEN_PER_THREAD)), WF_REGEN_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, cur[k], end, it);
         cur[k] = next;
       }
       st->wf_iterations++;
@@ -796,14 +801,18 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
       JT_CUDA(cudaEventSynchronize(st->poll_ev[batch & 1][k]));
       // per-launch duration of every extend launch of every pipeline (the roofline of bench.py divides the bytes of
       // ALL scene rays by this sum; launches of different pipelines overlap in wall time, each is timed on its stream)
+      float batch_ext_ms = 0.0f;
       for (int sub = 0; sub < poll_every; sub++) {
         const int evi = 16 * k + 2 * ((batch * poll_every + sub) % (2 * poll_every));
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, sc->ext_ev[evi], sc->ext_ev[evi + 1]) == cudaSuccess) sc->extend_ms += ms;
+        batch_ext_ms += ms;
         sc->extend_launches++;
       }
-      // poll_every is even, so cur[k] is the same queue at every poll
-      remaining[k] = std::min(remaining[k], hc[k * WF_C_TOTAL + WF_C_EXT(cur[k])]);
+      remaining[k] = std::min(remaining[k], st->wf[k].n - hc[k * WF_C_TOTAL + WF_C_DONE]);
+      if (iter_log)  // JT_ITER_LOG=<file>: batch, pipeline, queue length after the batch, extend ms of the batch, host ms
+        fprintf(iter_log, "%d %d %d %.4f %.3f\n", batch, k, hc[k * WF_C_TOTAL + WF_C_EXT(cur[k])], batch_ext_ms,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - iter_t0).count());
       if (remaining[k] == 0) active[k] = false;
       *any = *any || active[k];
     }
@@ -826,6 +835,10 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
         break;
       }
     }
+  }
+  if (iter_log) {
+    fprintf(iter_log, "end\n");
+    fclose(iter_log);
   }
   // later work on the main stream (download, the next range) waits for every pipeline
   for (int k = 1; k < npipe; k++) {
@@ -877,6 +890,7 @@ extern "C" int jt_trace_sample_range(jt_scene* sc, jt_state* st, const jt_params
   int rc = check_params(sc, p);
   if (rc) return rc;
   if (begin < 0 || end < begin) return jt_set_error(JT_ERR_INVALID, "bad sample range [%d, %d)", begin, end);
+  if (end >= (1 << 23)) return jt_set_error(JT_ERR_INVALID, "sample indices are limited to 2^23 - 1 (got %d)", end);
   if (end == begin) return JT_OK;
   if (st->has_pending && (begin != st->pending_end || !same_render_params(*p, st->pending_params))) {
     if ((rc = flush_state(st))) return rc;

@@ -79,14 +79,45 @@ JT_DEV void persist_init(PersistLane& L, const JtDevScene& S, f3 o, f3 d, float 
   L.tmin = tmin;
 }
 
-// One warp-uniform traversal episode: runs until every lane has finished its ray or (when `more` rays
-// are waiting) fewer than JT_FETCH_THRESHOLD lanes remain live. `live` is updated per lane.
-JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, const TravStack& stack, bool& live, bool more) {
+// Launch tail (tools/sim_persist_tail.py: 27 % of a full launch's warp iterations run after the queue is empty, at ~10
+// of 32 lanes; 66 % for a quarter-full queue): once nothing is left to fetch, a warp that is down to fewer than
+// JT_SUSPEND_BELOW live lanes SUSPENDS its stragglers instead of dragging them to the end at a few lanes per
+// instruction. The traversal state (closest hit so far, the pending node / triangle groups) is parked in the slot, the
+// slot goes straight to the next iteration's extend queue, and the next launch resumes it inside a full warp. A slot
+// holds one ray of one pixel at a time, so delaying it by an iteration changes no result. Every ray runs at least
+// JT_SUSPEND_MIN_ITERS loop iterations per launch (progress).
+#ifndef JT_SUSPEND_BELOW
+#define JT_SUSPEND_BELOW 0 /* 0 = never suspend (default: see the measurement in profiles/r02/tuning_variants.txt) */
+#endif
+#ifndef JT_SUSPEND_MIN_ITERS
+#define JT_SUSPEND_MIN_ITERS 6
+#endif
+#define JT_SUSPEND_STACK 16 /* parked stack entries per slot (8 B each); deeper lanes simply run on */
+#ifdef JT_EMU_COUNT
+// host emulation (single-lane warps that always find `more`): tests force a suspension every N iterations instead
+static int jt_emu_suspend_every = 0;
+JT_DEV bool persist_wants_suspend(bool more, int lanes, int iters) {
+  (void)more; (void)lanes;
+  return jt_emu_suspend_every > 0 && iters >= jt_emu_suspend_every;
+}
+#else
+JT_DEV bool persist_wants_suspend(bool more, int lanes, int iters) {
+  return JT_SUSPEND_BELOW > 0 && !more && lanes < JT_SUSPEND_BELOW && iters >= JT_SUSPEND_MIN_ITERS;
+}
+#endif
+
+// One warp-uniform traversal episode: runs until every lane has finished its ray, or (when `more` rays are waiting)
+// fewer than JT_FETCH_THRESHOLD lanes remain live, or (allow_suspend) the warp should park its stragglers: returns true
+// in that last case. `live` is updated per lane.
+JT_DEV bool persist_traverse(const JtDevScene& S, PersistLane& L, const TravStack& stack, bool& live, bool more,
+                             bool allow_suspend = false) {
   const unsigned FULL = 0xFFFFFFFFu;
-  for (;;) {
+  int iters = 0;
+  for (;; iters++) {
     unsigned am = __ballot_sync(FULL, live);
     if (am == 0u) break;
     if (more && __popc(am) < JT_FETCH_THRESHOLD) break;
+    if (allow_suspend && persist_wants_suspend(more, __popc(am), iters)) return true;
     // ---- A: one node step -------------------------------------------------------------------------
     if (live) {
       if (L.ngroup.y > 0x00FFFFFFu) {
@@ -173,6 +204,41 @@ JT_DEV void persist_traverse(const JtDevScene& S, PersistLane& L, const TravStac
       }
     }
   }
+  return false;
+}
+
+// Park / resume a live lane at the top of the traversal loop (tgroup is empty there; ngroup is the current entry).
+//   hit0 = {inst, elem, u, v}   hit1 = {t, wtri, entries | (blas_sp + 1) << 8, cur_inst}   entries = sp + 1 <= JT_SUSPEND_STACK
+JT_DEV bool persist_can_park(const PersistLane& L) { return L.sp + 1 <= JT_SUSPEND_STACK; }
+JT_DEV void persist_park(const PersistLane& L, const TravStack& stack, float4* hit0, float4* hit1, uint2* parked) {
+  *hit0 = make_float4(__int_as_float(L.best.inst), __int_as_float(L.best.elem), L.best.u, L.best.v);
+  *hit1 = make_float4(L.best.t, __int_as_float(L.best.wtri), __int_as_float((L.sp + 1) | ((L.blas_sp + 1) << 8)),
+                      __int_as_float(L.cur_inst));
+  for (int i = 0; i < L.sp; i++) parked[i] = stack.get(i);
+  parked[L.sp] = L.ngroup;
+}
+// after persist_init(L, ...) with the slot's world ray
+JT_DEV void persist_resume(PersistLane& L, const JtDevScene& S, const TravStack& stack, float4 hit0, float4 hit1,
+                           const uint2* parked) {
+  L.best.inst = __float_as_int(hit0.x);
+  L.best.elem = __float_as_int(hit0.y);
+  L.best.u = hit0.z;
+  L.best.v = hit0.w;
+  L.best.t = hit1.x;
+  L.best.wtri = __float_as_int(hit1.y);
+  if (L.best.inst >= 0) L.best_t = L.best.t;
+  const int packed = __float_as_int(hit1.z);
+  const int entries = packed & 0xFF;
+  L.blas_sp = (packed >> 8) - 1;
+  L.cur_inst = __float_as_int(hit1.w);
+  if (L.cur_inst >= 0) {  // the same arithmetic as at BLAS entry: identical instance-space ray
+    const JtInstanceRec& I = S.instances[L.cur_inst];
+    wide_ray_setup(L.R, xform_point(I.inv, L.wo), xform_vector(I.inv, L.wd));
+  }
+  L.sp = entries - 1;
+  for (int i = 0; i < L.sp; i++) stack.put(i, parked[i]);
+  L.ngroup = parked[L.sp];
+  L.tgroup = make_uint2(0u, 0u);
 }
 
 // Warp-aggregated fetch of the next queue indices for the lanes that `want` one. All 32 lanes call.

