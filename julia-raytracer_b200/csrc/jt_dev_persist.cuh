@@ -87,7 +87,7 @@ JT_DEV void persist_init(PersistLane& L, const JtDevScene& S, f3 o, f3 d, float 
 // holds one ray of one pixel at a time, so delaying it by an iteration changes no result. Every ray runs at least
 // JT_SUSPEND_MIN_ITERS loop iterations per launch (progress).
 #ifndef JT_SUSPEND_BELOW
-#define JT_SUSPEND_BELOW 0 /* 0 = never suspend (default: see the measurement in profiles/r02/tuning_variants.txt) */
+#define JT_SUSPEND_BELOW 8 /* 0 = never suspend; 8 / 12 / 16 / 24 measured in profiles/r02/tuning_variants.txt */
 #endif
 #ifndef JT_SUSPEND_MIN_ITERS
 #define JT_SUSPEND_MIN_ITERS 6

@@ -227,6 +227,19 @@ __constant__ uint32_t jt_c_prmt_magic = 0x43800000u;
 #else
 #define JT_PRMT_MAGIC 0x43800000u
 #endif
+// byte k of the result = 0xFF if bit 31 of word k is set, else 0x00
+JT_DEV uint32_t sign_bytes4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+#if defined(__CUDA_ARCH__) && !defined(JT_EMU_COUNT)
+  uint32_t ab, cd, r;
+  // selector nibble = 8 | byte index: replicate that byte's most significant bit
+  asm("prmt.b32 %0, %1, %2, 0x00FB;" : "=r"(ab) : "r"(a), "r"(b));
+  asm("prmt.b32 %0, %1, %2, 0x00FB;" : "=r"(cd) : "r"(c), "r"(d));
+  asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(r) : "r"(ab), "r"(cd));
+  return r;
+#else
+  return ((a >> 31) * 0xFFu) | ((b >> 31) * 0xFF00u) | ((c >> 31) * 0xFF0000u) | ((d >> 31) * 0xFF000000u);
+#endif
+}
 JT_DEV float byte_as_biased_float(uint32_t w, int i, uint32_t magic) {
   return __uint_as_float(__byte_perm(w, magic, 0x7604u | ((uint32_t)i << 4)));
 }
@@ -281,17 +294,26 @@ JT_DEV uint32_t wide_node_hits(const float4* __restrict__ wnodes, uint32_t node,
     const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
     const uint32_t inner_mask4 = (is_inner4 >> 4) * 7u;  // 0x07 in every internal byte
     const uint32_t bit_index4 = (meta4 ^ (oct4 & inner_mask4)) & 0x1F1F1F1Fu;
-    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    // The ray misses child j iff  max(t0x, t0y, t0z, tmin) > min(t1x, t1y, t1z, tmax), i.e. iff one of the three
+    // differences below is negative (none is ever NaN: the slab values are finite, tmin is, tmax is finite or +inf).
+    // Taking the clamps out of the min / max chains moves two operations per child from the ALU pipe (FMNMX), which
+    // bounds this loop together with the PRMT conversions, to the FMA pipe (FADD); the sign bits are OR-ed by one LOP3.
+    uint32_t sgn[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       float t0x = fmaf(byte_as_biased_float(nearx, j, magic), sx, alx), t1x = fmaf(byte_as_biased_float(farx, j, magic), sx, ahx);
       float t0y = fmaf(byte_as_biased_float(neary, j, magic), sy, aly), t1y = fmaf(byte_as_biased_float(fary, j, magic), sy, ahy);
       float t0z = fmaf(byte_as_biased_float(nearz, j, magic), sz, alz), t1z = fmaf(byte_as_biased_float(farz, j, magic), sz, ahz);
-      float lo = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tmin));
-      float hi = fminf(fminf(t1x, t1y), fminf(t1z, tmax));
-      uint32_t bits = byte_of(child_bits4, j) << byte_of(bit_index4, j);
-      hits |= (lo <= hi) ? bits : 0u;
+      float lo = fmaxf(fmaxf(t0x, t0y), t0z);
+      float hi = fminf(fminf(t1x, t1y), t1z);
+      sgn[j] = __float_as_uint(hi - lo) | __float_as_uint(tmax - lo) | __float_as_uint(hi - tmin);
     }
+    // the four sign bits, smeared over their bytes by PRMT's sign-replication mode, knock the missed children's bit
+    // counts out of the packed word at once (3 PRMT + 1 LOP3 instead of 4 FSETP + 4 SEL)
+    const uint32_t miss4 = sign_bytes4(sgn[0], sgn[1], sgn[2], sgn[3]);
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u & ~miss4;
+#pragma unroll
+    for (int j = 0; j < 4; j++) hits |= __byte_perm(child_bits4, 0u, 0x4440u + (uint32_t)j) << (byte_of(bit_index4, j) & 31u);
   }
   *ngroup_out = make_uint2(__float_as_uint(n1.x), (hits & 0xFF000000u) | imask);
   *tgroup_out = make_uint2(__float_as_uint(n1.y), hits & 0x00FFFFFFu);
