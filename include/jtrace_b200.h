@@ -187,7 +187,8 @@ typedef struct {
   int64_t wide_depth_top;      /* depth of the top-level wide BVH */
   int64_t wide_depth_blas;     /* deepest instanced BLAS */
   int64_t opened_instances;    /* instances opened into the top-level tree (flattened / braided; INTEGRATION.md knobs) */
-  int64_t _reserved[5];
+  int64_t wide_bvh_from_cache; /* 1 = the wide BVH came from the cache directory (jt_set_bvh_cache_dir), 0 = built */
+  int64_t _reserved[4];
 } jt_scene_stats;
 JT_API int jt_scene_get_stats(jt_scene* scene, jt_scene_stats* out);
 
@@ -306,6 +307,12 @@ JT_API int jt_probe_read_bandwidth(int device, int64_t bytes, int reps, float* g
  * bboxes = n x {min[3], max[3]} floats. nodes_out must hold 2*n+1 entries, primitives_out n. */
 JT_API int jt_make_bvh(const float* bboxes, int64_t n, int high_quality, jt_bvh_node* nodes_out,
                        int64_t* num_nodes_out, int64_t* primitives_out);
+
+/* N1: where jt_scene_create / jt_group_create keep finished wide BVHs (the expensive host step for
+ * instancing-heavy scenes: 4.7 s for ecosys' 16.8 M flattened records). Files are named by a hash of everything the
+ * builder reads (src/bvh.jl:66-304 replaced: shapes, instance frames, the host's BVHs, tuning knobs), written atomically,
+ * and ignored when they do not match. NULL or "" turns caching off (the default, unless JT_BVH_CACHE_DIR is set). */
+JT_API int jt_set_bvh_cache_dir(const char* dir);
 
 /* The whole host side natively (SURVEY.md 8f N2 and the host halves of N1 / N4), for hosts that are not Julia:
  *   jt_host_scene_load   = load_scene (src/sceneio.jl:25-93): the scene JSON, PLY shapes (src/shape.jl:78-124, quad

@@ -105,7 +105,7 @@ class jt_scene_stats(C.Structure):
                 ("inlined_instances", C.c_int64), ("instanced_instances", C.c_int64),
                 ("texture_bytes", C.c_int64), ("total_device_bytes", C.c_int64),
                 ("wide_depth_top", C.c_int64), ("wide_depth_blas", C.c_int64), ("opened_instances", C.c_int64),
-                ("_reserved", C.c_int64 * 5)]
+                ("wide_bvh_from_cache", C.c_int64), ("_reserved", C.c_int64 * 4)]
 
 
 class jt_group_stats(C.Structure):

@@ -59,6 +59,8 @@ def make_parser() -> argparse.ArgumentParser:
     p.add_argument("--gpu-devices", dest="gpu_devices", type=str, default="",
                    help="comma-separated CUDA device ids (or 'all') to shard the sample axis over, inside one "
                         "process (jt_group: scene replicated, fused peer-to-peer merge); empty = one device")
+    p.add_argument("--gpu-bvh-cache", dest="gpu_bvh_cache", type=str, default="",
+                   help="directory for finished wide BVHs (keyed by a hash of the scene geometry); empty = no cache")
     p.add_argument("--gpu-native-host", dest="gpu_native_host", type=_bool, default=False,
                    help="load the scene, build the BVH and the light CDFs inside the library (jt_host_scene_*) "
                         "instead of with the Python mirror; same bytes either way")
@@ -90,6 +92,7 @@ class Params:  # src/cli.jl:90-108
     gpu_integrator: str = "wavefront"
     gpu_devices: str = ""
     gpu_native_host: bool = False
+    gpu_bvh_cache: str = ""
 
     @staticmethod
     def from_args(ns: argparse.Namespace) -> "Params":

@@ -112,8 +112,8 @@ static int flush_scene(jt_scene* sc) {
   return JT_OK;
 }
 
-template <class T>
-static int upload(jt_scene* sc, const std::vector<T>& v, const T** out) {
+template <class T, class A>
+static int upload(jt_scene* sc, const std::vector<T, A>& v, const T** out) {
   *out = nullptr;
   size_t bytes = sizeof(T) * std::max<size_t>(v.size(), 1);
   void* p = nullptr;
@@ -203,6 +203,7 @@ static int scene_upload_impl(const JtStagedScene& staged, int device, jt_scene* 
   sc->stats.wide_depth_top = staged.depth;
   sc->stats.wide_depth_blas = staged.blas_depth;
   sc->stats.opened_instances = wide.flattened_instances;
+  sc->stats.wide_bvh_from_cache = staged.wide_from_cache ? 1 : 0;
   return JT_OK;
 }
 

@@ -394,8 +394,10 @@ JT_DEV float4 lerp4(float4 a, float4 b, float u) {
   float w = 1.0f - u;
   return make_float4(a.x * w + b.x * u, a.y * w + b.y * u, a.z * w + b.z * u, a.w * w + b.w * u);
 }
-JT_DEV void accumulate_sample(const DevState& st, const DevParams& P, bool has_env, int idx, int sample,
-                              const TraceOut& r, f3 ray_d) {
+// `old_*`: the pixel's accumulators as loaded by the caller (k_wf_regen issues these loads together with the slot's
+// other loads, before it knows whether it is the pixel's turn).
+JT_DEV void accumulate_loaded(const DevState& st, const DevParams& P, bool has_env, int idx, int sample, const TraceOut& r,
+                              f3 ray_d, float4 old_img, float4 old_alb, float4 old_nrm, int old_hits) {
   f3 radiance = r.radiance;
   if (!finite3(radiance)) radiance = f3{0.0f, 0.0f, 0.0f};
   float mx = max3(radiance);
@@ -421,14 +423,18 @@ JT_DEV void accumulate_sample(const DevState& st, const DevParams& P, bool has_e
   }
   if (P.accumulate == 0) {  // running mean, Q13
     float w = 1.0f / (float)(sample + 1);
-    st.image[idx] = lerp4(st.image[idx], img, w);
-    st.albedo[idx] = lerp4(st.albedo[idx], alb, w);
-    st.normal[idx] = lerp4(st.normal[idx], nrm, w);
+    st.image[idx] = lerp4(old_img, img, w);
+    st.albedo[idx] = lerp4(old_alb, alb, w);
+    st.normal[idx] = lerp4(old_nrm, nrm, w);
   } else {  // plain sums: what gets reduced across GPUs
-    float4 a = st.image[idx], b = st.albedo[idx], c = st.normal[idx];
+    float4 a = old_img, b = old_alb, c = old_nrm;
     st.image[idx] = make_float4(a.x + img.x, a.y + img.y, a.z + img.z, a.w + img.w);
     st.albedo[idx] = make_float4(b.x + alb.x, b.y + alb.y, b.z + alb.z, 0.0f);
     st.normal[idx] = make_float4(c.x + nrm.x, c.y + nrm.y, c.z + nrm.z, 0.0f);
   }
-  if (count) st.hits[idx] += 1;
+  if (count) st.hits[idx] = old_hits + 1;
+}
+JT_DEV void accumulate_sample(const DevState& st, const DevParams& P, bool has_env, int idx, int sample,
+                              const TraceOut& r, f3 ray_d) {
+  accumulate_loaded(st, P, has_env, idx, sample, r, ray_d, st.image[idx], st.albedo[idx], st.normal[idx], st.hits[idx]);
 }

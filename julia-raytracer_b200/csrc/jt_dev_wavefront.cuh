@@ -104,6 +104,22 @@ JT_DEV void wf_append(int* q, int* cnt, bool pred, int slot) {
   if (pred) q[base + __popc(m & ((1u << lane_id()) - 1u))] = slot;
 }
 
+// Two appends at once (shade: probe queue + next extend queue): both atomics are issued before either result is used, so
+// the warp waits for one L2 round trip instead of two. Must be reached by all 32 lanes.
+JT_DEV void wf_append2(int* qa, int* ca, bool pa, int* qb, int* cb, bool pb, int slot) {
+  const unsigned ma = __ballot_sync(0xFFFFFFFFu, pa), mb = __ballot_sync(0xFFFFFFFFu, pb);
+  if ((ma | mb) == 0u) return;
+  const int la = ma ? __ffs((int)ma) - 1 : 0, lb = mb ? __ffs((int)mb) - 1 : 0;
+  int base_a = 0, base_b = 0;
+  if (ma && (int)lane_id() == la) base_a = atomicAdd(ca, __popc(ma));
+  if (mb && (int)lane_id() == lb) base_b = atomicAdd(cb, __popc(mb));
+  base_a = __shfl_sync(0xFFFFFFFFu, base_a, la);
+  base_b = __shfl_sync(0xFFFFFFFFu, base_b, lb);
+  const unsigned below = (1u << lane_id()) - 1u;
+  if (pa) qa[base_a + __popc(ma & below)] = slot;
+  if (pb) qb[base_b + __popc(mb & below)] = slot;
+}
+
 // Same, into one of WF_NKEY queues selected by key (key < 0: no append). All 32 lanes must call.
 JT_DEV void wf_append_keyed(int* q_shade, int* counts, int n, int key, int slot) {
   unsigned valid = __ballot_sync(0xFFFFFFFFu, key >= 0);
@@ -220,16 +236,21 @@ JT_DEV int wf_regen_slot(const JtDevScene& S, const WfBuffers& B, const DevState
   const int pix = wf_slot_pixel(B, s);
   const int lp = pix - B.pixel_base;
   if (!(p.flags & WF_F_COMMITTED)) {
+    // every load the commit needs is issued before the turn is examined: one memory round trip instead of four
     const int turn = B.commit[lp];
+#ifdef JT_AB_NO_HOIST
+    if ((turn >> 8) != (int)p.sample || (turn & 255) == (epoch & 255)) return WF_REGEN_RETRY;
+#endif
+    const float4 rad = B.rad[s], a = B.alb[s], n = B.nrm[s];
+    const float4 old_img = st.image[pix], old_alb = st.albedo[pix], old_nrm = st.normal[pix];
+    const int old_hits = st.hits[pix];
     // an earlier sample of the pixel is still in flight, or was committed by this very launch
     if ((turn >> 8) != (int)p.sample || (turn & 255) == (epoch & 255)) return WF_REGEN_RETRY;
-    float4 rad = B.rad[s];
     TraceOut r;
     r.radiance = f3{rad.x, rad.y, rad.z};
     r.hit = (p.flags & WF_F_HIT) != 0u;
     f3 cam_d = f3{0.0f, 0.0f, 0.0f};
     if (r.hit) {
-      float4 a = B.alb[s], n = B.nrm[s];
       r.albedo = f3{a.x, a.y, a.z};
       r.normal = f3{n.x, n.y, n.z};
     } else {
@@ -241,7 +262,7 @@ JT_DEV int wf_regen_slot(const JtDevScene& S, const WfBuffers& B, const DevState
       f2 luv = rng.next2();
       cam_d = sample_camera(S.cameras[P.camera], pix % P.width, pix / P.width, P.width, P.height, puv, luv, P.tentfilter != 0).d;
     }
-    accumulate_sample(st, P, S.num_environments != 0, pix, (int)p.sample, r, cam_d);
+    accumulate_loaded(st, P, S.num_environments != 0, pix, (int)p.sample, r, cam_d, old_img, old_alb, old_nrm, old_hits);
     B.commit[lp] = WF_COMMIT_WORD((int)p.sample + 1, epoch);
   }
   if (wf_claim(S, B, P, s, pix, sample_end)) return WF_REGEN_QUEUED;
@@ -644,8 +665,12 @@ __global__ void __launch_bounds__(JT_SHADE_BLOCK, JT_SHADE_MINBLOCKS) k_wf_shade
       wf_end_sample(B, s, p, radiance);  // committed + regenerated by k_wf_regen
     }
   }
+#ifndef JT_AB_NO_APPEND2
+  wf_append2(B.q_probe, B.counts + WF_C_PROBE, to_probe, B.q_ext[next], B.counts + WF_C_EXT(next), to_extend, s);
+#else
   wf_append(B.q_probe, B.counts + WF_C_PROBE, to_probe, s);
   wf_append(B.q_ext[next], B.counts + WF_C_EXT(next), to_extend, s);
+#endif
   if (SAMPLER == 1 && MODE == MODE_WIDE) {
     unsigned lr = __reduce_add_sync(0xFFFFFFFFu, cnt.light_rays);
     if (lane_id() == 0u && lr) atomicAdd(counters + 2, (unsigned long long)lr);

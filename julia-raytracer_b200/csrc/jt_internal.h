@@ -5,6 +5,9 @@
 #include <vector_types.h>
 
 #include <string>
+#include <memory>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "../../include/jtrace_b200.h"
@@ -161,10 +164,24 @@ struct JtHostInstance {
   int shape, material;
   bool inlined;
 };
+// std::vector whose resize() leaves trivially constructible elements uninitialised: the multi-GB arrays of a flattened
+// scene are filled right after being sized (builder splice, cache read), and zeroing them first costs as much as the fill.
+template <class T>
+struct JtNoInitAlloc : std::allocator<T> {
+  template <class U>
+  struct rebind { using other = JtNoInitAlloc<U>; };
+  template <class U>
+  void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new ((void*)p) U; }
+  template <class U, class... Args>
+  void construct(U* p, Args&&... args) { ::new ((void*)p) U(std::forward<Args>(args)...); }
+};
+template <class T>
+using JtBigVec = std::vector<T, JtNoInitAlloc<T>>;
+
 struct JtWideResult {
-  std::vector<JtWideNode> nodes;
-  std::vector<JtWideTri> tris;
-  std::vector<uint32_t> tri_rank[8];   // per octant, indexed like tris
+  JtBigVec<JtWideNode> nodes;
+  JtBigVec<JtWideTri> tris;
+  JtBigVec<uint32_t> tri_rank[8];      // per octant, indexed like tris
   std::vector<uint32_t> inst_rank[8];  // per octant, indexed by instance
   std::vector<int32_t> shape_root;     // per shape: root node of its BLAS or -1
   int32_t top_root = -1;
@@ -187,7 +204,8 @@ struct JtStagedScene {
   std::vector<JtHostInstance> hinst;
   std::vector<JtInstanceRec> inst_recs;
   JtWideResult wide;
-  std::vector<uint32_t> tri_rank, inst_rank;
+  JtBigVec<uint32_t> tri_rank;  // [8][num_wtris]
+  std::vector<uint32_t> inst_rank;
   std::vector<float4> inst_bounds;
   std::vector<JtMaterialRec> mats;
   std::vector<JtTextureRec> texs;
@@ -200,6 +218,7 @@ struct JtStagedScene {
   std::vector<JtCameraRec> cams;
   std::vector<float> lut;
   int depth = 0, blas_depth = 0;
+  bool wide_from_cache = false;
   int32_t tlas_num_nodes = 0, num_instances = 0, num_environments = 0, num_lights = 0, num_cameras = 0;
 };
 struct JtStagedPointers {

@@ -14,7 +14,7 @@ from .lights import make_trace_lights
 from .scene import find_camera
 from .sceneio import load_scene, save_image, save_srgb8  # noqa: F401
 from . import _lib
-from .trace import DeviceGroup, DeviceScene, NativeHostScene, get_image, make_trace_state, trace_samples
+from .trace import DeviceGroup, DeviceScene, NativeHostScene, set_bvh_cache_dir, get_image, make_trace_state, trace_samples
 
 
 def format_seconds(seconds: float) -> str:
@@ -84,6 +84,8 @@ def main(params: Union[str, Params, None], device: int = 0, devices=None) -> Opt
         lights = make_trace_lights(scene, params)
     print("uploading scene to the GPU...")
     t0 = time.time()
+    if getattr(params, "gpu_bvh_cache", ""):
+        set_bvh_cache_dir(params.gpu_bvh_cache)
     devs = parse_devices(devices if devices is not None else getattr(params, "gpu_devices", ""))
     if len(devs) > 1:  # one host thread, N devices: the sample axis is sharded inside the library (jt_group)
         dscene = DeviceGroup(scene, bvh, lights, devs)

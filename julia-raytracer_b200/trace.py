@@ -39,6 +39,11 @@ def _counters_dict(c: A.jt_counters) -> dict:
                 extend_us=int(c.extend_kernel_us), extend_launches=int(c.extend_launches))
 
 
+def set_bvh_cache_dir(path: Optional[str]) -> None:
+    """Directory in which jt_scene_create keeps finished wide BVHs (None / "" = off). SURVEY.md 8f N1."""
+    _lib.check(_lib.lib().jt_set_bvh_cache_dir(str(path).encode() if path else None))
+
+
 class NativeHostScene:
     """load_scene + make_scene_bvh + make_trace_lights done inside the library (jt_host_scene_*, SURVEY.md 8f N2 and
     the host halves of N1 / N4): what a C or C++ host uses instead of sceneio.py / bvh.py / lights.py. The arrays are

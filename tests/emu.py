@@ -56,7 +56,7 @@ class Emu:
     def stats(self):
         out = np.zeros(8, np.int64)
         self.L.emu_stats(self.h, out.ctypes.data)
-        return dict(zip(["wide_nodes", "wide_tris", "inlined", "instanced", "depth_top", "depth_blas", "flattened"], map(int, out)))
+        return dict(zip(["wide_nodes", "wide_tris", "inlined", "instanced", "depth_top", "depth_blas", "flattened", "from_cache"], map(int, out)))
 
     def intersect(self, rays, traversal=0):
         rays = np.ascontiguousarray(rays, dtype=A.RAY_DTYPE)

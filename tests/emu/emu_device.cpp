@@ -50,6 +50,7 @@ EMU_API void emu_stats(void* h, int64_t* out) {
   out[6] = e->staged.wide.flattened_instances;
   out[4] = e->staged.depth;
   out[5] = e->staged.blas_depth;
+  out[7] = e->staged.wide_from_cache ? 1 : 0;
 }
 
 static void put_hit(jt_hit* o, const DHit& h) {

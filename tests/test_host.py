@@ -264,3 +264,37 @@ def test_header_structs_match_ctypes_mirror():
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     for n, s in zip(names, sizes):
         assert C.sizeof(getattr(A, n)) == s, (n, s, C.sizeof(getattr(A, n)))
+
+
+def test_wide_bvh_cache_round_trip(tmp_path, scenes, monkeypatch):
+    """N1: jt_stage_scene stores the finished wide BVH under a hash of the builder's inputs and finds it again; a damaged
+    or foreign file is ignored. Exercised through the host emulation (same jt_stage.cpp as the library)."""
+    import emu
+    import raygen
+    import orc
+    monkeypatch.setenv("JT_BVH_CACHE_DIR", str(tmp_path))
+    sc, bvh, lights = scenes("features1")
+    a = emu.Emu(sc, bvh, lights)
+    assert a.stats()["from_cache"] == 0
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 1 and files[0].startswith("jtwide_") and files[0].endswith(".bin")
+    b = emu.Emu(sc, bvh, lights)
+    assert b.stats()["from_cache"] == 1 and b.stats() == {**a.stats(), "from_cache": 1}
+    o = orc.Oracle(sc, bvh, lights)
+    p = orc.make_params(resolution=96)
+    w, h = o.make_state(p)
+    rays = raygen.camera_rays(o, p, w, h, 4000, seed=9)
+    rays = np.concatenate([rays, raygen.secondary_rays(rays, o.intersect(rays), seed=10)])
+    ha, hb = a.intersect(rays, 0), b.intersect(rays, 0)
+    assert ha.tobytes() == hb.tobytes()
+    # another scene gets another file; a truncated file is rebuilt, not trusted
+    sc2, bvh2, lights2 = scenes("cornellbox")
+    emu.Emu(sc2, bvh2, lights2)
+    assert len(os.listdir(tmp_path)) == 2
+    path = os.path.join(tmp_path, files[0])
+    data = open(path, "rb").read()
+    open(path, "wb").write(data[: len(data) // 2])
+    c = emu.Emu(sc, bvh, lights)
+    assert c.stats()["from_cache"] == 0 and os.path.getsize(path) == len(data)
+    monkeypatch.delenv("JT_BVH_CACHE_DIR")
+    assert emu.Emu(sc, bvh, lights).stats()["from_cache"] == 0
