@@ -761,7 +761,7 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
         // grids sized from the last polled number of slots that are not idle for good (an upper bound of every queue:
         // a slot appears at most once per iteration, and idle slots never come back within a range)
         unsigned ge = (unsigned)((remaining[k] + 127) / 128);
-        unsigned gs = (unsigned)((remaining[k] + 32 * WF_NKEY + JT_SHADE_BLOCK - 1) / JT_SHADE_BLOCK);
+        unsigned gs = (unsigned)((remaining[k] + JT_SHADE_BLOCK - 1) / JT_SHADE_BLOCK + WF_NKEY);  // every key's queue is padded to a whole block
         unsigned gpr = (unsigned)((remaining[k] + JT_PROBE_BLOCK - 1) / JT_PROBE_BLOCK);
         const int evi = 2 * (it % (2 * poll_every));
         JT_CUDA(cudaEventRecord(sc->ext_ev[16 * k + evi], q));

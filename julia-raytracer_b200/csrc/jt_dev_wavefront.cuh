@@ -238,9 +238,6 @@ JT_DEV int wf_regen_slot(const JtDevScene& S, const WfBuffers& B, const DevState
   if (!(p.flags & WF_F_COMMITTED)) {
     // every load the commit needs is issued before the turn is examined: one memory round trip instead of four
     const int turn = B.commit[lp];
-#ifdef JT_AB_NO_HOIST
-    if ((turn >> 8) != (int)p.sample || (turn & 255) == (epoch & 255)) return WF_REGEN_RETRY;
-#endif
     const float4 rad = B.rad[s], a = B.alb[s], n = B.nrm[s];
     const float4 old_img = st.image[pix], old_alb = st.albedo[pix], old_nrm = st.normal[pix];
     const int old_hits = st.hits[pix];
@@ -429,8 +426,8 @@ JT_DEV bool wf_roulette(f3& weight, WfPath& p, uint64_t key) {
 }
 
 // ---- shade ---------------------------------------------------------------------------------------------
-// One thread per queued slot; queues are laid out key after key, each padded to a warp multiple so a
-// warp only ever sees one material type.
+// One thread per queued slot; queues are laid out key after key, each padded to a block multiple so a
+// block only ever sees one material type.
 #ifndef JT_SHADE_BLOCK
 #define JT_SHADE_BLOCK 128
 #endif
@@ -457,30 +454,17 @@ JT_DEV bool wf_inline_mis(const JtDevScene& S, f3 position, f3 incoming, f3 f, f
   return true;
 }
 
-template <int SAMPLER, int MODE>
-__global__ void __launch_bounds__(JT_SHADE_BLOCK, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
-                                                  int sample_end, unsigned long long* counters) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  int key = -1, s = -1;
-  PathCounters cnt{0u, 0u};
-  {
-    int off = 0;
-#pragma unroll
-    for (int k = 0; k < WF_NKEY; k++) {
-      int c = B.counts[WF_C_SHADEK(k)];
-      int padded = (c + 31) & ~31;
-      if (key < 0 && t >= off && t < off + padded) {
-        if (t - off < c) {
-          key = k;
-          s = B.q_shade[(size_t)k * B.n + (t - off)];
-        } else {
-          key = -2;  // padding lane
-        }
-      }
-      off += padded;
-    }
-  }
-  bool to_extend = false, to_probe = false;
+// Per-material specialisation (KEY = the shading queue's material type, or -1 = decided at run time). Queues are padded
+// to BLOCK multiples, so a block only ever sees one key and jumps to the body compiled for it: the lobe switches of
+// jt_dev_shade.cuh fold to one case, the dead lobes leave the instruction stream (the generic kernel is 20.6 k SASS
+// instructions and 17 % of its stall samples were instruction-cache misses, profiles/r02/hot_lines_shade_r02f.txt).
+#ifndef JT_SHADE_SPECIALISE
+#define JT_SHADE_SPECIALISE 0 /* measured: 1-1.5 % slower (96 instead of 80 registers; profiles/r02/tuning_variants.txt) */
+#endif
+template <int SAMPLER, int MODE, int KEY>
+JT_DEV void wf_shade_slot(const JtDevScene& S, const WfBuffers& B, const DevParams& P, int s, int key_rt, bool& to_extend,
+                          bool& to_probe, PathCounters& cnt) {
+  const int key = KEY >= 0 ? KEY : key_rt;
   if (s >= 0) {
     const f3 zero = f3{0.0f, 0.0f, 0.0f};
     WfPath p = wf_load_ctl(B, s);
@@ -518,7 +502,8 @@ __global__ void __launch_bounds__(JT_SHADE_BLOCK, JT_SHADE_MINBLOCKS) k_wf_shade
       f3 outgoing = -ray.d;
       if (!in_volume) {
         const JtInstanceRec& I = S.instances[inst];
-        const JtMaterialRec& M = S.materials[I.material];
+        JtMaterialRec M = S.materials[I.material];  // a copy: scalarised, only the fields that are used get loaded
+        if (KEY >= 0) M.type = KEY;  // the queue key IS the material type: the lobe switches fold to one case
         ElemRef E = elem_ref(S, I, elem);
         f3 position = eval_position(S, I, E, hu, hv);
         f3 normal = eval_shading_normal(S, I, E, M, hu, hv, outgoing);
@@ -665,12 +650,48 @@ __global__ void __launch_bounds__(JT_SHADE_BLOCK, JT_SHADE_MINBLOCKS) k_wf_shade
       wf_end_sample(B, s, p, radiance);  // committed + regenerated by k_wf_regen
     }
   }
-#ifndef JT_AB_NO_APPEND2
-  wf_append2(B.q_probe, B.counts + WF_C_PROBE, to_probe, B.q_ext[next], B.counts + WF_C_EXT(next), to_extend, s);
-#else
-  wf_append(B.q_probe, B.counts + WF_C_PROBE, to_probe, s);
-  wf_append(B.q_ext[next], B.counts + WF_C_EXT(next), to_extend, s);
+}
+
+template <int SAMPLER, int MODE>
+__global__ void __launch_bounds__(JT_SHADE_BLOCK, JT_SHADE_MINBLOCKS) k_wf_shade(JtDevScene S, WfBuffers B, DevState st, DevParams P, int next,
+                                                  int sample_end, unsigned long long* counters) {
+  // block -> (key, first entry of the block inside that key's queue); every key's segment is a whole number of blocks
+  int key = -1, s = -1;
+  PathCounters cnt{0u, 0u};
+  {
+    int first_block = 0;
+#pragma unroll
+    for (int k = 0; k < WF_NKEY; k++) {
+      const int c = B.counts[WF_C_SHADEK(k)];
+      const int blocks = (c + JT_SHADE_BLOCK - 1) / JT_SHADE_BLOCK;
+      if (key < 0 && (int)blockIdx.x < first_block + blocks) {
+        key = k;
+        const int at = ((int)blockIdx.x - first_block) * JT_SHADE_BLOCK + (int)threadIdx.x;
+        if (at < c) s = B.q_shade[(size_t)k * B.n + at];
+      }
+      first_block += blocks;
+    }
+  }
+  bool to_extend = false, to_probe = false;
+#if JT_SHADE_SPECIALISE
+  if (SAMPLER == 1 && MODE == MODE_WIDE) {  // the benchmarked combination; the others share the generic body
+    switch (key) {
+      case 0: wf_shade_slot<SAMPLER, MODE, 0>(S, B, P, s, key, to_extend, to_probe, cnt); break;
+      case 1: wf_shade_slot<SAMPLER, MODE, 1>(S, B, P, s, key, to_extend, to_probe, cnt); break;
+      case 2: wf_shade_slot<SAMPLER, MODE, 2>(S, B, P, s, key, to_extend, to_probe, cnt); break;
+      case 3: wf_shade_slot<SAMPLER, MODE, 3>(S, B, P, s, key, to_extend, to_probe, cnt); break;
+      case 4: wf_shade_slot<SAMPLER, MODE, 4>(S, B, P, s, key, to_extend, to_probe, cnt); break;
+      case 5: wf_shade_slot<SAMPLER, MODE, 5>(S, B, P, s, key, to_extend, to_probe, cnt); break;
+      case 6: wf_shade_slot<SAMPLER, MODE, 6>(S, B, P, s, key, to_extend, to_probe, cnt); break;
+      case WF_KEY_MISS: wf_shade_slot<SAMPLER, MODE, WF_KEY_MISS>(S, B, P, s, key, to_extend, to_probe, cnt); break;
+      default: break;  // blocks beyond the queues; key 7 (gltfpbr) is rejected at staging
+    }
+  } else
 #endif
+  {
+    wf_shade_slot<SAMPLER, MODE, -1>(S, B, P, s, key, to_extend, to_probe, cnt);
+  }
+  wf_append2(B.q_probe, B.counts + WF_C_PROBE, to_probe, B.q_ext[next], B.counts + WF_C_EXT(next), to_extend, s);
   if (SAMPLER == 1 && MODE == MODE_WIDE) {
     unsigned lr = __reduce_add_sync(0xFFFFFFFFu, cnt.light_rays);
     if (lane_id() == 0u && lr) atomicAdd(counters + 2, (unsigned long long)lr);

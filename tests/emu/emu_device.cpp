@@ -204,7 +204,7 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
       run(1, [&] { k_wf_extend_persist(e->dev, B, cur, cnt); });
     } else run(ne, [&] { k_wf_extend<MODE_WIDE>(e->dev, B, cur, cnt); });
     int ns = 0;
-    for (int k = 0; k < WF_NKEY; k++) ns += (counts[WF_C_SHADEK(k)] + 31) & ~31;
+    for (int k = 0; k < WF_NKEY; k++) ns += counts[WF_C_SHADEK(k)];
     if (P.sampler == 1) {
       if (p->traversal == 1) run(ns, [&] { k_wf_shade<1, MODE_REF>(e->dev, B, st, P, next, end, cnt); });
       else run(ns, [&] { k_wf_shade<1, MODE_WIDE>(e->dev, B, st, P, next, end, cnt); });

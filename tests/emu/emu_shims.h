@@ -52,6 +52,7 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
 static inline void __syncwarp(unsigned = 0xFFFFFFFFu) {}
 #define JT_FETCH_THRESHOLD 1 /* single-lane warps */
 #define JT_SUSPEND_MIN_QUEUE 0
+#define JT_SHADE_BLOCK 1 /* one emulated thread per block: the shade kernel maps BLOCKS to material keys */
 template <class T>
 static inline T __shfl_up_sync(unsigned, T v, int) { return v; }
 template <class T>
