@@ -138,43 +138,95 @@ def run_reference_arm(args):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """SM clock + throttle reasons DURING the timed region (the profiling recipe's clocks line), every 200 ms.
+    In-process NVML (pynvml) when available: a handful of cheap driver queries per sample. The nvidia-smi fallback is
+    started BEFORE the warm-up steps (its start-up enumerates every GPU of the box and was seen to stall kernel
+    submission of the first timed step by ~0.2 s); only samples taken between mark_begin() and stop() are used."""
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []   # (time, sm_mhz, max_mhz, set of reasons)
         self.proc = None
+        self.nvml = None
+        self.t_begin = None
+        self._stop = threading.Event()
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES-relative index -> NVML handle through the CUDA device's UUID when torch knows it
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml = (pynvml, h)
+            threading.Thread(target=self._poll_nvml, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            threading.Thread(target=self._read_smi, daemon=True).start()
         except Exception:
             self.proc = None
 
-    def _read(self):
+    def _poll_nvml(self):
+        nv, h = self.nvml
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((time.perf_counter(), sm, mx, {k for k, b in bits.items() if mask & b}))
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def _read_smi(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            if len(r) > 7 and r[1].replace(".", "").isdigit():
+                mx = float(r[2]) if r[2].replace(".", "").isdigit() else None
+                self.rows.append((time.perf_counter(), float(r[1]), mx,
+                                  {nm for k, nm in enumerate(names) if r[4 + k].lower().startswith("active")}))
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if self.proc is None and self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampler unavailable"]}
         time.sleep(0.25)
-        self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        t_end = time.perf_counter()
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for r in self.rows if self.t_begin is None or self.t_begin <= r[0] <= t_end]
+        sm = [r[1] for r in rows]
+        mx = [r[2] for r in rows if r[2] is not None]
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) > 8:
-                for k, nm in enumerate(names):
-                    if r[5 + k].lower().startswith("active"):
-                        reasons.add(nm)
+        for r in rows:
+            reasons |= r[3]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "via": "nvml" if self.nvml else "nvidia-smi"}
 
 
 class _DevBuf:
@@ -303,6 +355,8 @@ def main():
         st.set_samples(n_samples)
 
     # ================================ leg 1: value (inputs resident, one merge + download at job end) ===============
+    clocks = ClockSampler(local_rank)
+    clocks.start()  # before the warm-up: its start-up cost stays out of the timed region
     for k in range(args.warmup):
         b, e = shard.step_range(k, world, rank, spp)
         trace.trace_sample_range(state, dscene, params, b, e)
@@ -311,8 +365,7 @@ def main():
     barrier()
     dscene.counters(reset=True)
     dscene.elapsed_ms()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark_begin()
     kernel_ms = 0.0
     t0 = time.perf_counter()
     for k in range(args.warmup, total_steps):
@@ -500,6 +553,11 @@ def main():
                               "uploaded once per render (see scene_upload), like the reference loads it once"},
             "scene_upload": upload,
             "gpu_launches": int(launches),
+            "scheduling": {"stolen_samples": int(c.get("stolen_samples", 0)), "resumed_rays": int(c.get("resumed_rays", 0)),
+                           "camera_paths": int(c["camera_paths"]), "scene_rays": int(c["scene_rays"]),
+                           "what": "rank 0, timed steps: samples traced by a path slot that started on another pixel "
+                                   "(work stealing) and closest-hit queries parked in a launch tail and resumed by the "
+                                   "next launch; neither changes a result bit (DESIGN.md 1.5)"},
             "scene_stats": stats,
         }
         if multi_gpu_check is not None:

@@ -164,7 +164,8 @@ typedef struct {
   uint64_t extend_kernel_us;  /* device time of the dominant kernel (extend = closest hit), summed over its launches,
                                  CUDA events on the launching streams */
   uint64_t extend_launches;   /* number of extend launches timed */
-  uint64_t _reserved[2];
+  uint64_t stolen_samples;    /* samples traced by a path slot that started the range on another pixel (work stealing) */
+  uint64_t resumed_rays;      /* closest-hit queries parked in a launch tail and resumed by the next launch */
 } jt_counters;
 
 typedef struct jt_scene jt_scene; /* device-resident scene: SceneData + SceneBvh + TraceLights */

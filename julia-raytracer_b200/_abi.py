@@ -96,7 +96,7 @@ class jt_hit(C.Structure):
 class jt_counters(C.Structure):
     _fields_ = [("camera_paths", C.c_uint64), ("scene_rays", C.c_uint64), ("light_rays", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("extend_kernel_us", C.c_uint64),
-                ("extend_launches", C.c_uint64), ("_reserved", C.c_uint64 * 2)]
+                ("extend_launches", C.c_uint64), ("stolen_samples", C.c_uint64), ("resumed_rays", C.c_uint64)]
 
 
 class jt_scene_stats(C.Structure):

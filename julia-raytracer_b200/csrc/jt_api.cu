@@ -53,6 +53,15 @@ extern "C" int jt_device_count(void) {
 // =================================================================================================
 // scene
 // =================================================================================================
+#define JT_MAX_PIPES 4
+// The host keeps JT_WF_LOOKAHEAD batches (of 4 wavefront iterations per pipeline) enqueued beyond the one whose queue
+// counters it is waiting for: one batch (~2.7 ms of GPU work at 1280x720) was not enough slack for a host thread that
+// gets descheduled for a few milliseconds; two cost one more batch of empty launches at the end of a range.
+#ifndef JT_WF_LOOKAHEAD
+#define JT_WF_LOOKAHEAD 2
+#endif
+#define JT_WF_RING (JT_WF_LOOKAHEAD + 1)
+#define JT_EXT_EVENTS (JT_MAX_PIPES * 2 * 4 * JT_WF_RING)
 struct jt_scene {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -61,11 +70,11 @@ struct jt_scene {
   std::vector<void*> allocs;
   JtDevScene dev;
   int num_cameras = 0, num_instances = 0;
-  unsigned long long* d_counters = nullptr;  // [0] camera paths [1] scene rays [2] light rays
+  unsigned long long* d_counters = nullptr;  // [0] camera paths [1] scene rays [2] light rays [3] stolen samples [4] resumed rays [7] jt_intersect fetch
   uint64_t launches = 0;
   unsigned persist_blocks = 0, intersect_blocks = 0;
   // device time of the dominant kernel (extend), measured with CUDA events around every launch
-  cudaEvent_t ext_ev[64] = {};  // [pipeline][16]: start/stop pairs around the extend launches of the last two batches
+  cudaEvent_t ext_ev[JT_EXT_EVENTS] = {};  // [pipeline][2 * 4 * JT_WF_RING]: start/stop pairs around the extend launches of the batches in flight
   double extend_ms = 0.0;
   uint64_t extend_launches = 0;
   std::vector<jt_state*> states;  // for flushing lazily batched sample ranges
@@ -73,7 +82,7 @@ struct jt_scene {
   int64_t device_bytes = 0;
 };
 
-#define JT_MAX_PIPES 4
+
 struct jt_state {
   jt_scene* scene = nullptr;
   int width = 0, height = 0, samples = 0;
@@ -87,7 +96,7 @@ struct jt_state {
   cudaEvent_t pipe_done[JT_MAX_PIPES] = {};
   std::vector<void*> wf_allocs;
   int* h_counts = nullptr;  // pinned mirror of the pipelines' counters (WF_C_TOTAL ints each), double-buffered
-  cudaEvent_t poll_ev[2][JT_MAX_PIPES] = {};
+  cudaEvent_t poll_ev[JT_WF_RING][JT_MAX_PIPES] = {};
   // download staging (allocated on first download)
   void* d_pack = nullptr;
   void* h_pack = nullptr;
@@ -156,7 +165,7 @@ static int scene_upload_impl(const JtStagedScene& staged, int device, jt_scene* 
   JT_CUDA(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
   JT_CUDA(cudaEventCreate(&sc->ev_start));
   JT_CUDA(cudaEventCreate(&sc->ev_stop));
-  for (int k = 0; k < 64; k++) JT_CUDA(cudaEventCreate(&sc->ext_ev[k]));
+  for (int k = 0; k < JT_EXT_EVENTS; k++) JT_CUDA(cudaEventCreate(&sc->ext_ev[k]));
   memset(&sc->dev, 0, sizeof(sc->dev));
   memset(&sc->stats, 0, sizeof(sc->stats));
 
@@ -273,6 +282,8 @@ extern "C" int jt_scene_counters(jt_scene* sc, jt_counters* out, int reset) {
   out->kernel_launches = sc->launches;
   out->extend_kernel_us = (uint64_t)(sc->extend_ms * 1000.0);  // microseconds in the extend (closest-hit) kernel
   out->extend_launches = sc->extend_launches;
+  out->stolen_samples = h[3];
+  out->resumed_rays = h[4];
   if (reset) {
     JT_CUDA(cudaMemset(sc->d_counters, 0, sizeof(h)));
     sc->launches = 0;
@@ -709,10 +720,9 @@ static int wf_prepare(jt_scene* sc, jt_state* st) {
     st->pipe_stream[k] = sc->stream;
     if (k > 0) JT_CUDA(cudaStreamCreateWithFlags(&st->pipe_stream[k], cudaStreamNonBlocking));
     JT_CUDA(cudaEventCreateWithFlags(&st->pipe_done[k], cudaEventDisableTiming));
-    JT_CUDA(cudaEventCreateWithFlags(&st->poll_ev[0][k], cudaEventDisableTiming));
-    JT_CUDA(cudaEventCreateWithFlags(&st->poll_ev[1][k], cudaEventDisableTiming));
+    for (int b = 0; b < JT_WF_RING; b++) JT_CUDA(cudaEventCreateWithFlags(&st->poll_ev[b][k], cudaEventDisableTiming));
   }
-  JT_CUDA(cudaHostAlloc((void**)&st->h_counts, 2 * JT_MAX_PIPES * WF_C_TOTAL * 4, cudaHostAllocDefault));
+  JT_CUDA(cudaHostAlloc((void**)&st->h_counts, JT_WF_RING * JT_MAX_PIPES * WF_C_TOTAL * 4, cudaHostAllocDefault));
   st->wf_ready = true;
   return JT_OK;
 }
@@ -727,7 +737,8 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
   if (rc) return rc;
   const int npipe = st->npipe;
   constexpr int poll_every = 4;
-  static_assert(poll_every % 2 == 0 && 4 * poll_every <= 16 && 16 * JT_MAX_PIPES <= 64, "poll_every: even (queue parity at every poll) and within ext_ev");
+  constexpr int ev_per_pipe = 2 * poll_every * JT_WF_RING;
+  static_assert(poll_every == 4 && ev_per_pipe * JT_MAX_PIPES == JT_EXT_EVENTS, "ext_ev holds the start/stop events of every batch in flight");
   int cur[JT_MAX_PIPES], remaining[JT_MAX_PIPES];
   bool active[JT_MAX_PIPES];
   // the other pipelines start after everything already enqueued on the main stream
@@ -763,15 +774,15 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
         unsigned ge = (unsigned)((remaining[k] + 127) / 128);
         unsigned gs = (unsigned)((remaining[k] + JT_SHADE_BLOCK - 1) / JT_SHADE_BLOCK + WF_NKEY);  // every key's queue is padded to a whole block
         unsigned gpr = (unsigned)((remaining[k] + JT_PROBE_BLOCK - 1) / JT_PROBE_BLOCK);
-        const int evi = 2 * (it % (2 * poll_every));
-        JT_CUDA(cudaEventRecord(sc->ext_ev[16 * k + evi], q));
+        const int evi = 2 * (it % (poll_every * JT_WF_RING));
+        JT_CUDA(cudaEventRecord(sc->ext_ev[ev_per_pipe * k + evi], q));
         if (MODE == MODE_WIDE) {
           unsigned gp = std::min<unsigned>((unsigned)((remaining[k] + JT_PERSIST_BLOCK - 1) / JT_PERSIST_BLOCK), pgrid);
           k_wf_extend_persist<<<gp, JT_PERSIST_BLOCK, 0, q>>>(sc->dev, B, cur[k], sc->d_counters);
         } else {
           k_wf_extend<MODE><<<ge, 128, 0, q>>>(sc->dev, B, cur[k], sc->d_counters);
         }
-        JT_CUDA(cudaEventRecord(sc->ext_ev[16 * k + evi + 1], q));
+        JT_CUDA(cudaEventRecord(sc->ext_ev[ev_per_pipe * k + evi + 1], q));
         if (P.sampler == 1) {
           k_wf_shade<1, MODE><<<gs, JT_SHADE_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
           k_wf_probe<MODE><<<gpr, JT_PROBE_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
@@ -780,31 +791,31 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
           k_wf_shade<2, MODE><<<gs, JT_SHADE_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, next, end, sc->d_counters);
           sc->launches += 3;
         }
-        k_wf_regen<<<(unsigned)((B.n + WF_REGEN_BLOCK * WF_REGEN_PER_THREAD - 1) / (WF_REGEN_BLOCK * WF_REGEN_PER_THREAD)), WF_REGEN_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, cur[k], end, it);
+        k_wf_regen<<<(unsigned)((B.n + WF_REGEN_BLOCK * WF_REGEN_PER_THREAD - 1) / (WF_REGEN_BLOCK * WF_REGEN_PER_THREAD)), WF_REGEN_BLOCK, 0, q>>>(sc->dev, B, st->dev, P, cur[k], end, it, sc->d_counters);
         cur[k] = next;
       }
       st->wf_iterations++;
     }
-    int* hc = st->h_counts + (size_t)(batch & 1) * JT_MAX_PIPES * WF_C_TOTAL;
+    int* hc = st->h_counts + (size_t)(batch % JT_WF_RING) * JT_MAX_PIPES * WF_C_TOTAL;
     for (int k = 0; k < npipe; k++) {
       if (!active[k]) continue;
       JT_CUDA(cudaMemcpyAsync(hc + k * WF_C_TOTAL, st->wf[k].counts, WF_C_TOTAL * 4, cudaMemcpyDeviceToHost, st->pipe_stream[k]));
-      JT_CUDA(cudaEventRecord(st->poll_ev[batch & 1][k], st->pipe_stream[k]));
+      JT_CUDA(cudaEventRecord(st->poll_ev[batch % JT_WF_RING][k], st->pipe_stream[k]));
     }
     return JT_OK;
   };
   // returns through *any whether some pipeline still has queued rays after `batch`
   auto collect_batch = [&](int batch, bool polled[JT_MAX_PIPES], bool* any) -> int {
-    const int* hc = st->h_counts + (size_t)(batch & 1) * JT_MAX_PIPES * WF_C_TOTAL;
+    const int* hc = st->h_counts + (size_t)(batch % JT_WF_RING) * JT_MAX_PIPES * WF_C_TOTAL;
     *any = false;
     for (int k = 0; k < npipe; k++) {
       if (!polled[k]) continue;
-      JT_CUDA(cudaEventSynchronize(st->poll_ev[batch & 1][k]));
+      JT_CUDA(cudaEventSynchronize(st->poll_ev[batch % JT_WF_RING][k]));
       // per-launch duration of every extend launch of every pipeline (the roofline of bench.py divides the bytes of
       // ALL scene rays by this sum; launches of different pipelines overlap in wall time, each is timed on its stream)
       float batch_ext_ms = 0.0f;
       for (int sub = 0; sub < poll_every; sub++) {
-        const int evi = 16 * k + 2 * ((batch * poll_every + sub) % (2 * poll_every));
+        const int evi = ev_per_pipe * k + 2 * ((batch * poll_every + sub) % (poll_every * JT_WF_RING));
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, sc->ext_ev[evi], sc->ext_ev[evi + 1]) == cudaSuccess) sc->extend_ms += ms;
         batch_ext_ms += ms;
@@ -820,19 +831,24 @@ static int launch_wavefront(jt_scene* sc, jt_state* st, const DevParams& P, int 
     return JT_OK;
   };
   {
-    bool polled[2][JT_MAX_PIPES];
+    bool polled[JT_WF_RING][JT_MAX_PIPES];
     int rc2;
-    for (int k = 0; k < JT_MAX_PIPES; k++) polled[0][k] = polled[1][k] = false;
-    for (int k = 0; k < npipe; k++) polled[0][k] = active[k];
-    if ((rc2 = enqueue_batch(0))) return rc2;
-    for (int batch = 1;; batch++) {
-      for (int k = 0; k < npipe; k++) polled[batch & 1][k] = active[k];
+    for (int b = 0; b < JT_WF_RING; b++)
+      for (int k = 0; k < JT_MAX_PIPES; k++) polled[b][k] = false;
+    // prologue: JT_WF_LOOKAHEAD batches in flight before the first wait
+    for (int batch = 0; batch < JT_WF_LOOKAHEAD; batch++) {
+      for (int k = 0; k < npipe; k++) polled[batch % JT_WF_RING][k] = active[k];
+      if ((rc2 = enqueue_batch(batch))) return rc2;
+    }
+    for (int batch = JT_WF_LOOKAHEAD;; batch++) {
+      for (int k = 0; k < JT_MAX_PIPES; k++) polled[batch % JT_WF_RING][k] = k < npipe && active[k];
       if ((rc2 = enqueue_batch(batch))) return rc2;
       bool any = false;
-      if ((rc2 = collect_batch(batch - 1, polled[(batch - 1) & 1], &any))) return rc2;
+      if ((rc2 = collect_batch(batch - JT_WF_LOOKAHEAD, polled[(batch - JT_WF_LOOKAHEAD) % JT_WF_RING], &any))) return rc2;
       if (!any) {
-        // the batch just enqueued ran on empty queues; drain its polls so the events / staging can be reused
-        if ((rc2 = collect_batch(batch, polled[batch & 1], &any))) return rc2;
+        // the batches already enqueued ran on empty queues; drain their polls so the events / staging can be reused
+        for (int b = batch - JT_WF_LOOKAHEAD + 1; b <= batch; b++)
+          if ((rc2 = collect_batch(b, polled[b % JT_WF_RING], &any))) return rc2;
         break;
       }
     }

@@ -218,6 +218,7 @@ static unsigned long long jt_emu_steals = 0;  // host emulation: samples traced 
 #define WF_REGEN_QUEUED 1  /* a new sample was started: the slot joins the next extend queue */
 #define WF_REGEN_RETRY 2   /* waiting for the pixel's turn, or found nothing to steal yet: visit again next iteration */
 #define WF_REGEN_DONE 3    /* nothing left to start anywhere: idle for good */
+#define WF_REGEN_STOLEN 4  /* like QUEUED, with a sample of another slot's pixel */
 
 JT_DEV bool wf_claim(const JtDevScene& S, const WfBuffers& B, const DevParams& P, int s, int pix, int sample_end) {
   const int lp = pix - B.pixel_base;
@@ -276,7 +277,7 @@ JT_DEV int wf_regen_slot(const JtDevScene& S, const WfBuffers& B, const DevState
 #ifdef JT_EMU_COUNT
         jt_emu_steals++;
 #endif
-        return WF_REGEN_QUEUED;
+        return WF_REGEN_STOLEN;
       }
     }
     if (!(p.flags & WF_F_COMMITTED)) {
@@ -357,7 +358,7 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
   bool live = false, more = true, parked = false;
   bool allow_suspend = B.parked != nullptr && count >= JT_SUSPEND_MIN_QUEUE;
   int s = -1;
-  unsigned nrays = 0u;
+  unsigned nrays = 0u, nresumed = 0u;
   for (;;) {
     __syncwarp();
     int key = -1;
@@ -389,6 +390,7 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
         if (r1.z != 0.0f) {  // a ray suspended by the previous launch: pick its traversal up where it stopped
           persist_resume(L, S, stack, B.hit0[s], B.hit1[s], B.parked + (size_t)s * JT_SUSPEND_STACK);
           (&B.ray1[s].x)[2] = 0.0f;
+          nresumed++;
         }
       }
       if (__ballot_sync(FULL, want && idx < 0)) more = false;
@@ -409,6 +411,8 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
   }
   unsigned total = __reduce_add_sync(FULL, nrays);
   if (lane_id() == 0u && total) atomicAdd(counters + 1, (unsigned long long)total);
+  total = __reduce_add_sync(FULL, nresumed);
+  if (lane_id() == 0u && total) atomicAdd(counters + 4, (unsigned long long)total);
 }
 
 // Bounce bookkeeping shared by shade (delta / naive / volume-free finishes) and probe:
@@ -502,8 +506,13 @@ JT_DEV void wf_shade_slot(const JtDevScene& S, const WfBuffers& B, const DevPara
       f3 outgoing = -ray.d;
       if (!in_volume) {
         const JtInstanceRec& I = S.instances[inst];
-        JtMaterialRec M = S.materials[I.material];  // a copy: scalarised, only the fields that are used get loaded
-        if (KEY >= 0) M.type = KEY;  // the queue key IS the material type: the lobe switches fold to one case
+        const JtMaterialRec& Mg = S.materials[I.material];
+        JtMaterialRec Mk;  // specialised bodies: a copy whose type is a compile-time constant (the queue key IS the
+        if (KEY >= 0) {    // material type), so the lobe switches fold to one case; scalarised, dead fields never load
+          Mk = Mg;
+          Mk.type = KEY;
+        }
+        const JtMaterialRec& M = KEY >= 0 ? Mk : Mg;
         ElemRef E = elem_ref(S, I, elem);
         f3 position = eval_position(S, I, E, hu, hv);
         f3 normal = eval_shading_normal(S, I, E, M, hu, hv, outgoing);
@@ -743,7 +752,7 @@ __global__ void __launch_bounds__(JT_PROBE_BLOCK, JT_PROBE_MINBLOCKS) k_wf_probe
 #endif
 #ifndef JT_EMU_COUNT
 __global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(JtDevScene S, WfBuffers B, DevState st, DevParams P, int cur,
-                                                             int sample_end, int epoch) {
+                                                             int sample_end, int epoch, unsigned long long* counters) {
   __shared__ int warp_sums[WF_REGEN_BLOCK / 32];
   __shared__ int flagged[WF_REGEN_BLOCK * WF_REGEN_PER_THREAD];  // flagged slots of this block, in slot order
   const int next = cur ^ 1;
@@ -796,7 +805,7 @@ __global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(JtDevScene S, WfBuf
   }
   __syncthreads();
   // consecutive lanes take consecutive flagged slots (= neighbouring pixels, mostly): coalesced accumulator updates
-  int done = 0;
+  int done = 0, stolen = 0;
   for (int base = warp * 32; base < total; base += WF_REGEN_BLOCK) {
     const int j = base + (int)lane_id();
     int slot = -1, what = 0;
@@ -805,10 +814,13 @@ __global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(JtDevScene S, WfBuf
       what = wf_regen_slot(S, B, st, P, slot, cur, sample_end, epoch);
       if (what != WF_REGEN_RETRY) B.regen[slot] = 0;
       done += what == WF_REGEN_DONE;
+      stolen += what == WF_REGEN_STOLEN;
     }
-    wf_append(B.q_ext[next], B.counts + WF_C_EXT(next), what == WF_REGEN_QUEUED, slot);
+    wf_append(B.q_ext[next], B.counts + WF_C_EXT(next), what == WF_REGEN_QUEUED || what == WF_REGEN_STOLEN, slot);
   }
   done = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)done);
+  stolen = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)stolen);
   if (lane_id() == 0u && done) atomicAdd(B.counts + WF_C_DONE, done);
+  if (lane_id() == 0u && stolen) atomicAdd(counters + 3, (unsigned long long)stolen);
 }
 #endif

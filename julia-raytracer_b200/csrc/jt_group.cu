@@ -329,6 +329,8 @@ extern "C" int jt_group_counters(jt_group* g, jt_counters* out, int reset) {
     out->light_rays += c.light_rays;
     out->kernel_launches += c.kernel_launches;
     out->extend_launches += c.extend_launches;
+    out->stolen_samples += c.stolen_samples;
+    out->resumed_rays += c.resumed_rays;
     if (c.extend_kernel_us > out->extend_kernel_us) out->extend_kernel_us = c.extend_kernel_us;
   }
   return JT_OK;

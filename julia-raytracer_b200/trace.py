@@ -36,7 +36,8 @@ def to_jt_params(params: Params, accumulate: int = 0) -> A.jt_params:
 def _counters_dict(c: A.jt_counters) -> dict:
     return dict(camera_paths=int(c.camera_paths), scene_rays=int(c.scene_rays),
                 light_rays=int(c.light_rays), kernel_launches=int(c.kernel_launches),
-                extend_us=int(c.extend_kernel_us), extend_launches=int(c.extend_launches))
+                extend_us=int(c.extend_kernel_us), extend_launches=int(c.extend_launches),
+                stolen_samples=int(c.stolen_samples), resumed_rays=int(c.resumed_rays))
 
 
 def set_bvh_cache_dir(path: Optional[str]) -> None:

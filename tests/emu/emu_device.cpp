@@ -221,7 +221,7 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
       if (regen[sl]) {
         int what = wf_regen_slot(e->dev, B, st, P, sl, cur, end, iterations);
         if (what != WF_REGEN_RETRY) regen[sl] = 0;
-        if (what == WF_REGEN_QUEUED) B.q_ext[next][B.counts[WF_C_EXT(next)]++] = sl;
+        if (what == WF_REGEN_QUEUED || what == WF_REGEN_STOLEN) B.q_ext[next][B.counts[WF_C_EXT(next)]++] = sl;
         if (what == WF_REGEN_DONE) counts[WF_C_DONE]++;
       }
     counts[WF_C_EXT(cur)] = 0; counts[WF_C_PROBE] = 0; counts[WF_C_FETCH] = 0;

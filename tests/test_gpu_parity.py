@@ -609,3 +609,34 @@ def test_odd_image_sizes_are_bit_exact(pair, res):
             else:
                 wide_mode_check(f"cornellbox {res}px sampler {sampler}", o, d, op, img, ref["image"], 3)
             st.close()
+
+
+@pytest.mark.gpu
+def test_scheduling_counters_and_their_invariance(pair):
+    """Work stealing and launch-tail suspension are live on the GPU (the counters say so) and change no bit: a render
+    whose ranges are cut differently -- so that other slots trace other samples and other rays get parked -- ends in the
+    same accumulators, and both equal the reference-order traversal (bit-exact vs the oracle elsewhere in this file)."""
+    o, d = pair("features1")
+    p = _params(resolution=640, samples=24, batch=24)
+    d.counters(reset=True)
+    a = trace.make_trace_state(d, p)
+    trace.trace_sample_range(a, d, p, 0, 24)
+    a.sync()
+    c = d.counters(reset=True)
+    assert c["camera_paths"] == a.width * a.height * 24
+    assert c["stolen_samples"] > 0.05 * c["camera_paths"], c  # the sky pixels finish early and help the others
+    assert c["resumed_rays"] > 0, c
+    b = trace.make_trace_state(d, p)
+    for lo, hi in ((0, 5), (5, 6), (6, 19), (19, 24)):
+        trace.trace_sample_range(b, d, p, lo, hi)
+        d.synchronize()
+    b.sync()
+    for k in ("image", "albedo", "normal", "hits"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    pr = _params(resolution=640, samples=24, batch=24, gpu_traversal="reference")
+    r = trace.make_trace_state(d, pr)
+    trace.trace_sample_range(r, d, pr, 0, 24)
+    r.sync()
+    differing = np.abs(a.image - r.image).max(axis=-1) > 1e-4
+    assert differing.mean() <= WIDE_PIXEL_FRACTION_BOUND, differing.mean()
+    assert np.array_equal(a.hits, r.hits) or differing.any()
