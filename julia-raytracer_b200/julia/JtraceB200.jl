@@ -147,8 +147,11 @@ and create the device twin of `state` (the TraceState `make_trace_state` returne
 `make_trace_state` (src/jtrace.jl:69). The library copies everything before returning.
 """
 function gpu_scene(scene::SceneData, bvh::SceneBvh, lights::TraceLights, state::TraceState, params::Params;
-                   devices::Vector{<:Integer} = [0], traversal::Integer = 0, seed::Integer = 0)::GpuScene
+                   devices::Vector{<:Integer} = [0], traversal::Integer = 0, seed::Integer = 0,
+                   bvh_cache_dir::AbstractString = "")::GpuScene
     check_layouts()
+    # N1: keep finished wide BVHs on disk (hash-named, atomically written); "" leaves caching to JT_BVH_CACHE_DIR
+    bvh_cache_dir == "" || check(ccall((:jt_set_bvh_cache_dir, LIB), Cint, (Cstring,), bvh_cache_dir))
     cams = [JtCamera(c) for c in scene.cameras]
     # vertex index vectors are Vector{SVector{k,Int64}}: reinterpret as flat Int64
     shapes = JtShapeDesc[]

@@ -9,7 +9,7 @@ for name in ['emu_create','emu_destroy','emu_last_error','emu_stats','emu_inters
     pass
 emu._LIB = None
 real = emu.lib()
-for name in ['emu_create','emu_destroy','emu_last_error','emu_stats','emu_intersect','emu_intersect_instance','emu_trace_range','emu_trace_wavefront','emu_wide_counts']:
+for name in ['emu_create','emu_destroy','emu_last_error','emu_stats','emu_intersect','emu_intersect_instance','emu_trace_range','emu_trace_wavefront','emu_wide_counts','emu_set_suspend_every','emu_resumed_rays','emu_stolen_samples']:
     f = getattr(L, name); g = getattr(real, name); f.restype = g.restype; f.argtypes = g.argtypes
 emu._LIB = L
 bvhm=importlib.import_module('julia-raytracer_b200.bvh'); lm=importlib.import_module('julia-raytracer_b200.lights')
@@ -24,6 +24,16 @@ for s in ['synthetic_all','synthetic_one','cornellbox','features1','classroom','
         for trav in (0,1):
             p=orc.make_params(resolution=32, samples=2, batch=2, sampler=sampler, traversal=trav)
             e.trace(p,32,max(1,int(32/ float(sc.cameras[0].aspect))),0,2,wavefront=True); e.trace(p,32,max(1,int(32/float(sc.cameras[0].aspect))),0,2,wavefront=False)
+    # round 2: park / resume of every ray every 2 traversal steps + a longer range with stolen samples
+    if s != 'ecosys':
+        p=orc.make_params(resolution=32, samples=8, batch=8, sampler=1, traversal=0)
+        hh=max(1,int(32/float(sc.cameras[0].aspect)))
+        plain=e.trace(p,32,hh,0,8,wavefront=True)
+        L.emu_set_suspend_every(2)
+        parked=e.trace(p,32,hh,0,8,wavefront=True)
+        L.emu_set_suspend_every(0)
+        assert np.array_equal(plain['image'], parked['image'])
+        print('   resumed', L.emu_resumed_rays(1), 'stolen', L.emu_stolen_samples(1), flush=True)
     print('asan ok', s, flush=True)
 # braided / flattened instance paths on small scenes (entry records at BLAS sub-trees, instance-space leaf tests)
 for braid in ('1', '16'):
