@@ -683,8 +683,26 @@ static DevParams dev_params(const jt_params* p, const jt_state* st) {
 
 static unsigned persist_grid(jt_scene* sc);
 
+// Experiment knob (JT_CARVEOUT = per cent of the unified L1 / shared memory given to shared memory): one preference for
+// every wavefront kernel, so that kernels of the two pipelines never ask an SM for different configurations.
+static void wf_set_carveout() {
+  static bool done = false;
+  if (done) return;
+  done = true;
+  const char* e = getenv("JT_CARVEOUT");
+  if (!e) return;
+  const int pct = atoi(e);
+  cudaFuncSetAttribute(k_wf_extend_persist, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(k_wf_regen, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(k_wf_generate, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(k_wf_shade<1, MODE_WIDE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(k_wf_shade<2, MODE_WIDE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  cudaFuncSetAttribute(k_wf_probe<MODE_WIDE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+}
+
 static int wf_prepare(jt_scene* sc, jt_state* st) {
   if (st->wf_ready) return JT_OK;
+  wf_set_carveout();
   const size_t total = (size_t)st->width * st->height;
   int npipe = getenv("JT_PIPELINES") ? atoi(getenv("JT_PIPELINES")) : JT_DEFAULT_PIPES;
   npipe = std::max(1, std::min(JT_MAX_PIPES, npipe));
