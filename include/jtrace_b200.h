@@ -309,6 +309,19 @@ JT_API int jt_probe_read_bandwidth(int device, int64_t bytes, int reps, float* g
 JT_API int jt_make_bvh(const float* bboxes, int64_t n, int high_quality, jt_bvh_node* nodes_out,
                        int64_t* num_nodes_out, int64_t* primitives_out);
 
+/* N4: make_trace_lights (src/trace.jl:117-187) on the GPU. Element weights (shape-local triangle / quad
+ * areas, max(texel) * sin(theta) per environment texel) by one thread per element; the CDF stays the reference's
+ * SEQUENTIAL Float32 prefix sum (a warp replays the host loop's additions in order), so the arrays are bit-identical to
+ * the host builders'. `desc` needs cameras / lights / bvh not to be set. The returned descriptors (valid until
+ * jt_lights_destroy) go into jt_scene_desc.lights. Flags: JT_LIGHTS_ENV_LUMINANCE weights environment texels by
+ * max(R, G, B) instead of the reference's max(R, G, B, A = 1) (quirk Q8: with texels <= 1 the reference's CDF ignores
+ * the image): unbiased, lower variance under a bright sun, NOT the reference's sample set. */
+#define JT_LIGHTS_ENV_LUMINANCE 1
+typedef struct jt_lights jt_lights;
+JT_API int jt_lights_create(const jt_scene_desc* desc, int device, int flags, jt_lights** out);
+JT_API int jt_lights_desc(jt_lights* lights, const jt_light_desc** descs, int64_t* count);
+JT_API void jt_lights_destroy(jt_lights* lights);
+
 /* N1: where jt_scene_create / jt_group_create keep finished wide BVHs (the expensive host step for
  * instancing-heavy scenes: 4.7 s for ecosys' 16.8 M flattened records). Files are named by a hash of everything the
  * builder reads (src/bvh.jl:66-304 replaced: shapes, instance frames, the host's BVHs, tuning knobs), written atomically,

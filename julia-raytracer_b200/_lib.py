@@ -26,6 +26,7 @@ EXPORTS = [
     "jt_group_state_download", "jt_group_state_download_srgb8", "jt_probe_read_bandwidth",
     "jt_host_scene_load", "jt_host_scene_build", "jt_host_scene_desc", "jt_host_scene_find_camera",
     "jt_host_scene_num_notes", "jt_host_scene_note", "jt_host_scene_destroy", "jt_set_bvh_cache_dir",
+    "jt_lights_create", "jt_lights_desc", "jt_lights_destroy",
 ]
 
 
@@ -76,6 +77,10 @@ def lib() -> C.CDLL:
     L.jt_intersect_device.argtypes = [vp, vp, i64, C.c_int, vp]
     L.jt_make_bvh.argtypes = [vp, i64, C.c_int, vp, C.POINTER(i64), vp]
     L.jt_set_bvh_cache_dir.argtypes = [C.c_char_p]
+    L.jt_lights_create.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.jt_lights_desc.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.jt_lights_destroy.argtypes = [vp]
+    L.jt_lights_destroy.restype = None
     L.jt_host_scene_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.jt_host_scene_build.argtypes = [vp, C.c_int]
     L.jt_host_scene_desc.argtypes = [vp, C.POINTER(C.POINTER(A.jt_scene_desc))]

@@ -61,6 +61,11 @@ def make_parser() -> argparse.ArgumentParser:
                         "process (jt_group: scene replicated, fused peer-to-peer merge); empty = one device")
     p.add_argument("--gpu-bvh-cache", dest="gpu_bvh_cache", type=str, default="",
                    help="directory for finished wide BVHs (keyed by a hash of the scene geometry); empty = no cache")
+    p.add_argument("--gpu-device-lights", dest="gpu_device_lights", type=_bool, default=False,
+                   help="build the light CDFs on the GPU (jt_lights_create: bit-identical to make_trace_lights)")
+    p.add_argument("--gpu-env-importance", dest="gpu_env_importance", type=_bool, default=False,
+                   help="with --gpu-device-lights: weight environment texels by max(R, G, B) instead of the reference's "
+                        "max(R, G, B, A = 1) (quirk Q8); unbiased, but no longer the reference's sample set")
     p.add_argument("--gpu-native-host", dest="gpu_native_host", type=_bool, default=False,
                    help="load the scene, build the BVH and the light CDFs inside the library (jt_host_scene_*) "
                         "instead of with the Python mirror; same bytes either way")
@@ -92,6 +97,8 @@ class Params:  # src/cli.jl:90-108
     gpu_integrator: str = "wavefront"
     gpu_devices: str = ""
     gpu_native_host: bool = False
+    gpu_device_lights: bool = False
+    gpu_env_importance: bool = False
     gpu_bvh_cache: str = ""
 
     @staticmethod

@@ -10,7 +10,7 @@ from typing import Optional, Union
 
 from .bvh import make_scene_bvh
 from .cli import Params, parse_cli_args
-from .lights import make_trace_lights
+from .lights import make_trace_lights, make_trace_lights_device
 from .scene import find_camera
 from .sceneio import load_scene, save_image, save_srgb8  # noqa: F401
 from . import _lib
@@ -81,7 +81,10 @@ def main(params: Union[str, Params, None], device: int = 0, devices=None) -> Opt
         bvh = make_scene_bvh(scene, params.highqualitybvh, params.noparallel)
         print(f"built bvh in {format_seconds(time.time() - t0)}")
         print("making lights...")
-        lights = make_trace_lights(scene, params)
+        if getattr(params, "gpu_device_lights", False):  # N4: element weights + sequential CDFs on the GPU
+            lights = make_trace_lights_device(scene, device, env_luminance=bool(getattr(params, "gpu_env_importance", False)))
+        else:
+            lights = make_trace_lights(scene, params)
     print("uploading scene to the GPU...")
     t0 = time.time()
     if getattr(params, "gpu_bvh_cache", ""):

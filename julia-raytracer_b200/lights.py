@@ -71,3 +71,36 @@ def make_trace_lights(scene: SceneData, params=None) -> List[TraceLight]:
             cdf = _seq_cumsum((value * _sin_f32(th.astype(np.float32))).astype(np.float32))
         lights.append(TraceLight(invalid_id, handle + 1, np.ascontiguousarray(cdf)))
     return lights
+
+
+JT_LIGHTS_ENV_LUMINANCE = 1
+
+
+def make_trace_lights_device(scene: SceneData, device: int = 0, env_luminance: bool = False) -> List[TraceLight]:
+    """`make_trace_lights` on the GPU (jt_lights_create): element weights in parallel, the CDF as the
+    reference's sequential Float32 prefix sum, so the arrays equal make_trace_lights' bit for bit. `env_luminance`
+    weights environment texels by max(R, G, B) instead of max(R, G, B, A) (quirk Q8; not the reference's sample set)."""
+    import ctypes as C
+
+    from . import _abi as A
+    from . import _lib
+    from .flatten import FlatScene
+
+    L = _lib.lib()
+    flat = FlatScene(scene, None, None)
+    h = C.c_void_p()
+    _lib.check(L.jt_lights_create(flat.byref(), device, JT_LIGHTS_ENV_LUMINANCE if env_luminance else 0, C.byref(h)))
+    try:
+        descs, n = C.c_void_p(), C.c_int64()
+        _lib.check(L.jt_lights_desc(h, C.byref(descs), C.byref(n)))
+        arr = C.cast(descs, C.POINTER(A.jt_light_desc))
+        out = []
+        for i in range(n.value):
+            d = arr[i]
+            cdf = np.zeros(d.num_elements, np.float32)
+            if d.num_elements:
+                C.memmove(cdf.ctypes.data, d.elements_cdf, 4 * d.num_elements)
+            out.append(TraceLight(int(d.instance), int(d.environment), cdf))
+        return out
+    finally:
+        L.jt_lights_destroy(h)

@@ -640,3 +640,43 @@ def test_scheduling_counters_and_their_invariance(pair):
     differing = np.abs(a.image - r.image).max(axis=-1) > 1e-4
     assert differing.mean() <= WIDE_PIXEL_FRACTION_BOUND, differing.mean()
     assert np.array_equal(a.hits, r.hits) or differing.any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cornellbox", "classroom", "features1", "materials1", "ecosys", "synthetic_all", "bathroom1"])
+def test_device_light_setup_is_bit_identical(scenes, name):
+    """N4: make_trace_lights on the GPU (jt_lights_create: parallel element weights, sequential Float32 prefix sums replayed
+    by a warp) returns the host builder's arrays bit for bit: same lights, same order, same CDFs (src/trace.jl:117-187)."""
+    lm = importlib.import_module("julia-raytracer_b200.lights")
+    sc, _, host = scenes(name)
+    dev = lm.make_trace_lights_device(sc, 0)
+    assert [(l.instance, l.environment) for l in dev] == [(l.instance, l.environment) for l in host]
+    assert len(dev) > 0
+    for a, b in zip(dev, host):
+        assert a.elements_cdf.dtype == np.float32 and a.elements_cdf.shape == b.elements_cdf.shape
+        assert a.elements_cdf.tobytes() == b.elements_cdf.tobytes(), (name, a.instance, a.environment)
+
+
+@pytest.mark.gpu
+def test_env_importance_flag_is_unbiased_and_uses_the_image(scenes):
+    """Quirk Q8 behind a flag (JT_LIGHTS_ENV_LUMINANCE): the environment CDF follows max(R, G, B) of the texels instead
+    of max(R, G, B, A = 1). Another sample set, the same expectation: the converged means agree."""
+    lm = importlib.import_module("julia-raytracer_b200.lights")
+    sc, bvh, host = scenes("features1")
+    flagged = lm.make_trace_lights_device(sc, 0, env_luminance=True)
+    env = [i for i, l in enumerate(host) if l.environment != -1][0]
+    ref_w = np.diff(host[env].elements_cdf.astype(np.float64))
+    new_w = np.diff(flagged[env].elements_cdf.astype(np.float64))
+    assert (new_w >= -1e-6).all() and not np.allclose(ref_w / ref_w.sum(), new_w / new_w.sum(), atol=1e-9)
+    p = _params(resolution=160, samples=256, batch=256)
+    images = []
+    for lights in (host, flagged):
+        d = trace.DeviceScene(sc, bvh, lights, 0)
+        try:
+            st = trace.make_trace_state(d, p)
+            trace.trace_samples(st, d, None, None, p)
+            images.append(st.image[:, :3].astype(np.float64).copy())
+        finally:
+            d.close()
+    a, b = images
+    assert abs(a.mean() - b.mean()) <= 0.01 * a.mean(), (a.mean(), b.mean())

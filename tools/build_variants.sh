@@ -11,10 +11,10 @@ make -s -C $SRC   # host objects (jt_stage.o, jt_wide_bvh.o, jt_host_bvh.o) are 
 build_one() {
   name=${1%%=*}; flags=${1#*=}
   d=$(mktemp -d)
-  for f in jt_api jt_group jt_probe; do
+  for f in jt_api jt_group jt_probe jt_lights; do
     nvcc $NVFLAGS $flags -I$SRC -c $SRC/$f.cu -o $d/$f.o
   done
-  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/variants/$name.so $d/jt_api.o $d/jt_group.o $d/jt_probe.o \
+  nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/variants/$name.so $d/jt_api.o $d/jt_group.o $d/jt_probe.o $d/jt_lights.o \
      $SRC/jt_host_bvh.o $SRC/jt_wide_bvh.o $SRC/jt_stage.o $SRC/jt_host_scene.o -lz -cudart static -ccbin /usr/bin/g++ -Xcompiler -fopenmp,-pthread
   rm -rf $d
   echo "built variants/$name.so  [$flags]"
