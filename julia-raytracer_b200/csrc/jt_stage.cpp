@@ -199,13 +199,13 @@ struct WideHash {
   template <class T>
   void vec(const std::vector<T>& v) { bytes(v.data(), v.size() * sizeof(T)); }
 };
-static const uint32_t kWideCacheVersion = 4;  // bump when the builder or the record layouts change
+static const uint32_t kWideCacheVersion = 5;  // bump when the builder or the record layouts change
 static uint64_t wide_cache_key(const std::vector<JtHostShape>& shapes, const std::vector<JtHostInstance>& inst,
                                const std::vector<jt_bvh_node>& tlas_nodes, const std::vector<int64_t>& tlas_prims) {
   if (bvh_cache_dir().empty()) return 0;
   WideHash H;
   H.word(kWideCacheVersion);
-  for (const char* knob : {"JT_BRAID_MAX", "JT_BRAID_MIN_INSTANCES", "JT_LEAF_MAX", "JT_TRI_COST", "JT_BUILD_PARALLEL_MIN"}) {
+  for (const char* knob : {"JT_BRAID_MAX", "JT_BRAID_MIN_INSTANCES", "JT_LEAF_MAX", "JT_TRI_COST", "JT_BUILD_PARALLEL_MIN", "JT_COLLAPSE"}) {
     const char* e = getenv(knob);
     H.bytes(e ? e : "", e ? strlen(e) : 0);
   }

@@ -490,12 +490,129 @@ class Collapser {
     for (int64_t e = 0; e < s.num_elements(); e++) element_records(s, e, inst, erank, recs, t);
   }
 
+  // ---- which binary nodes become the (up to) 8 children of a wide node ------------------------------------------------
+  // Default: dynamic programming over the binary tree (after Ylitie, Karras & Laine 2017, sec. 3.1, adapted to this
+  // layout where a leaf of <= 3 records is a child slot, not a node). F(n, i) = least expected cost of representing
+  // the subtree of n with at most i child slots of ONE wide node:
+  //   F(n, 1) = leaf(n) ? A_n * P_n * c_tri  :  A_n * c_node + D(n, 8)         (n becomes a wide node of its own)
+  //   F(n, i) = min(F(n, 1), D(n, i)),   D(n, i) = min_{0<k<i} F(left, k) + F(right, i - k)   (n is dissolved)
+  // with A the surface area (visit probability), c_node = one wide node step, c_tri = tri_cost_ / 8 of it per record --
+  // the same currency as the SAH build above. JT_COLLAPSE=greedy restores "open the largest child until 8" (round 1).
+  struct Dp {
+    float f[8];
+    uint8_t k[8];  // k[i - 1]: 0 = n takes one slot, else its left child gets k of the i slots
+  };
+  std::vector<Dp> dp_;
+  bool use_dp_ = false;
+  void compute_dp(const Tree& t, int root) {
+    use_dp_ = false;
+    const char* mode = getenv("JT_COLLAPSE");
+    const size_t nn = (size_t)t.next_node.load();
+    if ((mode && !strcmp(mode, "greedy")) || nn > ((size_t)6 << 20)) return;  // 40 B per node: giant flattened trees stay greedy
+    dp_.assign(nn, Dp());
+    const float c_node = 8.0f, c_tri = tri_cost_;
+    std::vector<std::pair<int, int>> st;  // (node, phase)
+    st.push_back({root, 0});
+    while (!st.empty()) {
+      auto [n, phase] = st.back();
+      st.pop_back();
+      const BNode& b = t.nodes[(size_t)n];
+      Dp& d = dp_[(size_t)n];
+      if (b.leaf()) {
+        const float c = b.box.area() * (float)b.count * c_tri;
+        for (int i = 0; i < 8; i++) {
+          d.f[i] = c;
+          d.k[i] = 0;
+        }
+        continue;
+      }
+      if (phase == 0) {
+        st.push_back({n, 1});
+        st.push_back({b.left, 0});
+        st.push_back({b.right, 0});
+        continue;
+      }
+      const Dp& L = dp_[(size_t)b.left];
+      const Dp& R = dp_[(size_t)b.right];
+      float dist[9];
+      uint8_t arg[9];
+      for (int i = 2; i <= 8; i++) {
+        float best = std::numeric_limits<float>::infinity();
+        int bk = 1;
+        for (int k = 1; k < i; k++) {
+          const float c = L.f[k - 1] + R.f[i - k - 1];
+          if (c < best) {
+            best = c;
+            bk = k;
+          }
+        }
+        dist[i] = best;
+        arg[i] = (uint8_t)bk;
+      }
+      const float own = b.box.area() * c_node + dist[8];
+      d.f[0] = own;
+      d.k[0] = 0;
+      for (int i = 2; i <= 8; i++) {
+        if (dist[i] < own) {
+          d.f[i - 1] = dist[i];
+          d.k[i - 1] = arg[i];
+        } else {
+          d.f[i - 1] = own;
+          d.k[i - 1] = 0;
+        }
+      }
+      d.k[7] = arg[8];  // a wide node rooted here always opens n itself
+    }
+    use_dp_ = true;
+  }
+  void dp_gather(const Tree& t, int n, int slots, int* kids, int* nkids) const {
+    const BNode& b = t.nodes[(size_t)n];
+    const int k = b.leaf() ? 0 : dp_[(size_t)n].k[slots - 1];
+    if (k == 0 || slots == 1) {
+      kids[(*nkids)++] = n;
+      return;
+    }
+    dp_gather(t, b.left, k, kids, nkids);
+    dp_gather(t, b.right, slots - k, kids, nkids);
+  }
+
   // ---- emit a wide BVH from a binary tree; returns the root index in out_->nodes ---------------------------
   // The binary tree is cut into jobs: the top of the tree is expanded breadth-first by one thread until a few
   // hundred subtrees are open, those are emitted in parallel into private sinks (local indices), and everything is
   // spliced into out_ in job order -- the result does not depend on the thread count.
+  // The traversal stack bounds the depth of the wide tree (jt_stage.cpp checks 2 * (top + BLAS levels) + 4 entries); the
+  // dynamic programme does not, and now and then prefers long chains of sparsely filled nodes (coffee: 20 + 16 levels).
+  // Such a tree is emitted again with the greedy rule.
+  static constexpr int kMaxDpDepth = 13;
+  int wide_depth(int root) const {
+    int best = 0;
+    std::vector<std::pair<int, int>> st;
+    st.push_back({root, 1});
+    while (!st.empty()) {
+      auto [n, d] = st.back();
+      st.pop_back();
+      best = std::max(best, d);
+      const JtWideNode& w = out_->nodes[(size_t)n];
+      const int k = __builtin_popcount(w.imask);
+      for (int i = 0; i < k; i++) st.push_back({(int)w.child_base + i, d + 1});
+    }
+    return best;
+  }
   int emit(const Tree& t, int root) {
     if (root < 0) return -1;
+    compute_dp(t, root);
+    const size_t G0 = out_->nodes.size(), T0 = out_->tris.size();
+    int r = emit_tree(t, root);
+    if (use_dp_ && wide_depth(r) > kMaxDpDepth) {
+      out_->nodes.resize(G0);
+      out_->tris.resize(T0);
+      for (int o = 0; o < 8; o++) out_->tri_rank[o].resize(T0);
+      use_dp_ = false;
+      r = emit_tree(t, root);
+    }
+    return r;
+  }
+  int emit_tree(const Tree& t, int root) {
     Sink top;
     top.nodes.push_back(JtWideNode());
     std::vector<Work> open;
@@ -571,6 +688,10 @@ class Collapser {
     const BNode& top = t.nodes[(size_t)bnode];
     if (top.leaf()) {
       kids[nkids++] = bnode;
+    } else if (use_dp_) {
+      const int k = dp_[(size_t)bnode].k[7];
+      dp_gather(t, top.left, k, kids, &nkids);
+      dp_gather(t, top.right, 8 - k, kids, &nkids);
     } else {
       kids[nkids++] = top.left;
       kids[nkids++] = top.right;
