@@ -205,7 +205,7 @@ static uint64_t wide_cache_key(const std::vector<JtHostShape>& shapes, const std
   if (bvh_cache_dir().empty()) return 0;
   WideHash H;
   H.word(kWideCacheVersion);
-  for (const char* knob : {"JT_BRAID_MAX", "JT_BRAID_MIN_INSTANCES", "JT_LEAF_MAX", "JT_TRI_COST", "JT_BUILD_PARALLEL_MIN", "JT_COLLAPSE"}) {
+  for (const char* knob : {"JT_BRAID_MAX", "JT_BRAID_MIN_INSTANCES", "JT_LEAF_MAX", "JT_TRI_COST", "JT_BUILD_PARALLEL_MIN", "JT_COLLAPSE", "JT_COLLAPSE_DP_MAX_NODES"}) {
     const char* e = getenv(knob);
     H.bytes(e ? e : "", e ? strlen(e) : 0);
   }

@@ -504,11 +504,14 @@ class Collapser {
   };
   std::vector<Dp> dp_;
   bool use_dp_ = false;
+  size_t dp_max_nodes_ = (size_t)6 << 20;
   void compute_dp(const Tree& t, int root) {
     use_dp_ = false;
     const char* mode = getenv("JT_COLLAPSE");
     const size_t nn = (size_t)t.next_node.load();
-    if ((mode && !strcmp(mode, "greedy")) || nn > ((size_t)6 << 20)) return;  // 40 B per node: giant flattened trees stay greedy
+    // 40 B of tables per binary node: JT_COLLAPSE_DP_MAX_NODES caps the trees it is used on
+    const size_t cap = getenv("JT_COLLAPSE_DP_MAX_NODES") ? (size_t)atoll(getenv("JT_COLLAPSE_DP_MAX_NODES")) : dp_max_nodes_;
+    if ((mode && !strcmp(mode, "greedy")) || nn > cap) return;
     dp_.assign(nn, Dp());
     const float c_node = 8.0f, c_tri = tri_cost_;
     std::vector<std::pair<int, int>> st;  // (node, phase)

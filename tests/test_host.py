@@ -298,3 +298,22 @@ def test_wide_bvh_cache_round_trip(tmp_path, scenes, monkeypatch):
     assert c.stats()["from_cache"] == 0 and os.path.getsize(path) == len(data)
     monkeypatch.delenv("JT_BVH_CACHE_DIR")
     assert emu.Emu(sc, bvh, lights).stats()["from_cache"] == 0
+
+
+def test_collapse_rule_changes_the_tree_not_the_hits(scenes, monkeypatch):
+    """The wide BVH's topology is free (tie ranks come from the reference tree): the dynamic-programming collapse and the
+    greedy one give different trees and the same hits, bit for bit."""
+    import emu
+    import raygen
+    sc, bvh, lights = scenes("features1")
+    o = orc.Oracle(sc, bvh, lights)
+    p = orc.make_params(resolution=96)
+    w, h = o.make_state(p)
+    rays = raygen.camera_rays(o, p, w, h, 6000, seed=21)
+    rays = np.concatenate([rays, raygen.secondary_rays(rays, o.intersect(rays), seed=22)])
+    dp = emu.Emu(sc, bvh, lights)
+    monkeypatch.setenv("JT_COLLAPSE", "greedy")
+    greedy = emu.Emu(sc, bvh, lights)
+    assert dp.stats()["wide_nodes"] < greedy.stats()["wide_nodes"]
+    assert dp.intersect(rays, 0).tobytes() == greedy.intersect(rays, 0).tobytes()
+    raygen.check_wide_vs_reference(dp.intersect(rays, 0), o.intersect(rays))
