@@ -29,8 +29,30 @@
 #include "jt_dev_persist.cuh"
 #include "jt_dev_trace.cuh"
 
-#define WF_NKEY 9     /* material types 0..7 + miss */
+// Shading queues: one per (material type, predicted MIS coin) pair + one for misses. The path sampler splits every
+// non-delta bounce in half -- BSDF sampling or light sampling, decided by one RNG draw (src/trace.jl:366-377) -- and the
+// two halves share no code until eval_bsdfcos. The draw's index is known when the ray is created (camera: draw 4;
+// bounce: the creator's counter, + 1 if the probe kernel will still play Russian roulette, + 2 inside a medium), so the
+// creator evaluates it and leaves the bit in the ray record; the extend kernel files the hit under (type, coin).
+// A wrong prediction (a stochastic-opacity draw comes first) only costs coherence: shading redraws the coin itself.
+#ifndef JT_COIN_QUEUES
+#define JT_COIN_QUEUES 1
+#endif
+#define WF_TYPE_MISS 8 /* what the shading body calls the miss key */
+#if JT_COIN_QUEUES
+#define WF_NKEY 17
+#define WF_KEY_MISS 16
+#define WF_QUEUE_KEY(type, coin) (((type) << 1) | (coin))
+#define WF_KEY_TYPE(key) ((key) >> 1)
+#else
+#define WF_NKEY 9 /* material types 0..7 + miss */
 #define WF_KEY_MISS 8
+#define WF_QUEUE_KEY(type, coin) (type)
+#define WF_KEY_TYPE(key) (key)
+#endif
+// ray1.z carries two bits (as raw integer bits): 1 = suspended traversal to resume, 2 = predicted coin
+#define WF_RAY_SUSPENDED 1
+#define WF_RAY_COIN 2
 // counter slots (ints). Every counter sits on its own 128-byte line: they are all hit by one atomic per warp per
 // kernel, and counters sharing a line would serialise in one L2 slice.
 #define WF_CS 32 /* ints between counters */
@@ -60,7 +82,7 @@ struct WfField {
 };
 struct WfBuffers {
   WfField<float4, 4> ray0;  // o.xyz, d.x
-  WfField<float4, 4> ray1;  // d.y, d.z, suspended (1 = hit0 / hit1 / parked hold a traversal to resume), bits(pixel)
+  WfField<float4, 4> ray1;  // d.y, d.z, bits(WF_RAY_SUSPENDED | WF_RAY_COIN), bits(pixel)
   WfField<float4, 4> hit0;  // bits(inst), bits(elem), u, v
   WfField<float4, 4> hit1;  // t_hit, -, -, -
   WfField<float4, 4> wgt;   // weight.xyz, -
@@ -171,8 +193,9 @@ JT_DEV void wf_start_sample(const JtDevScene& S, const WfBuffers& B, const DevPa
   f2 luv = rng.next2();
   int i = pix % P.width, j = pix / P.width;
   DRay ray = sample_camera(S.cameras[P.camera], i, j, P.width, P.height, puv, luv, P.tentfilter != 0);
+  const int coin = (JT_COIN_QUEUES && P.sampler == 1 && jt_rng_float(rng.key, rng.draw) < 0.5f) ? WF_RAY_COIN : 0;
   B.ray0[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
-  B.ray1[s] = make_float4(ray.d.y, ray.d.z, 0.0f, __int_as_float(pix));
+  B.ray1[s] = make_float4(ray.d.y, ray.d.z, __int_as_float(coin), __int_as_float(pix));
   B.wgt[s] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
   B.rad[s] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   WfPath p;
@@ -323,7 +346,7 @@ __global__ void __launch_bounds__(128) k_wf_extend(JtDevScene S, WfBuffers B, in
     if (h.inst >= 0) {
       B.hit0[s] = make_float4(__int_as_float(h.inst), __int_as_float(h.elem), h.u, h.v);
       B.hit1[s] = make_float4(h.t, 0.0f, 0.0f, 0.0f);
-      key = S.materials[S.instances[h.inst].material].type;
+      key = WF_QUEUE_KEY(S.materials[S.instances[h.inst].material].type, (__float_as_int(r1.z) & WF_RAY_COIN) ? 1 : 0);
     } else {
       B.hit0[s] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.0f, 0.0f);
       key = WF_KEY_MISS;
@@ -357,7 +380,7 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
   PersistLane L;
   bool live = false, more = true, parked = false;
   bool allow_suspend = B.parked != nullptr && count >= JT_SUSPEND_MIN_QUEUE;
-  int s = -1;
+  int s = -1, coin = 0;  // coin: predicted MIS coin of the lane's ray (queue key), from the ray record
   unsigned nrays = 0u, nresumed = 0u;
   for (;;) {
     __syncwarp();
@@ -366,7 +389,7 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
       if (L.best.inst >= 0) {
         B.hit0[s] = make_float4(__int_as_float(L.best.inst), __int_as_float(L.best.elem), L.best.u, L.best.v);
         B.hit1[s] = make_float4(L.best.t, 0.0f, 0.0f, 0.0f);
-        key = S.materials[S.instances[L.best.inst].material].type;
+        key = WF_QUEUE_KEY(S.materials[S.instances[L.best.inst].material].type, coin);
       } else {
         B.hit0[s] = make_float4(__int_as_float(-1), __int_as_float(-1), 0.0f, 0.0f);
         key = WF_KEY_MISS;
@@ -387,9 +410,11 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
         persist_init(L, S, f3{r0.x, r0.y, r0.z}, f3{r0.w, r1.x, r1.y}, JT_RAY_EPS, INFINITY, S.wide_root, -1);
         live = S.wide_root >= 0;
         if (!live) L.best.inst = -1;
-        if (r1.z != 0.0f) {  // a ray suspended by the previous launch: pick its traversal up where it stopped
+        const int rbits = __float_as_int(r1.z);
+        coin = (rbits & WF_RAY_COIN) ? 1 : 0;
+        if (rbits & WF_RAY_SUSPENDED) {  // a ray suspended by the previous launch: pick its traversal up where it stopped
           persist_resume(L, S, stack, B.hit0[s], B.hit1[s], B.parked + (size_t)s * JT_SUSPEND_STACK);
-          (&B.ray1[s].x)[2] = 0.0f;
+          (&B.ray1[s].x)[2] = __int_as_float(rbits & ~WF_RAY_SUSPENDED);
           nresumed++;
         }
       }
@@ -400,7 +425,7 @@ __global__ void __launch_bounds__(JT_PERSIST_BLOCK, JT_EXTEND_MINBLOCKS) k_wf_ex
     if (persist_traverse(S, L, stack, live, more, allow_suspend)) {
       if (live && persist_can_park(L)) {
         persist_park(L, stack, &B.hit0[s], &B.hit1[s], B.parked + (size_t)s * JT_SUSPEND_STACK);
-        (&B.ray1[s].x)[2] = 1.0f;
+        (&B.ray1[s].x)[2] = __int_as_float(WF_RAY_SUSPENDED | (coin ? WF_RAY_COIN : 0));
         live = false;
         parked = true;
       }
@@ -480,7 +505,7 @@ JT_DEV void wf_shade_slot(const JtDevScene& S, const WfBuffers& B, const DevPara
     f3 weight = f3{w4.x, w4.y, w4.z}, radiance = f3{rad4.x, rad4.y, rad4.z};
     bool alive = true;
     p.bounce += 1;  // top of the while loop, src/trace.jl:295-297
-    if (key == WF_KEY_MISS) {
+    if (key == WF_TYPE_MISS) {
       if (p.bounce > 0 || !P.envhidden) radiance = radiance + weight * eval_environment(S, ray.d);
       alive = false;
     } else {
@@ -650,7 +675,14 @@ JT_DEV void wf_shade_slot(const JtDevScene& S, const WfBuffers& B, const DevPara
     p.draw = rng.draw;
     if (alive) {
       B.ray0[s] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.d.x);
-      B.ray1[s] = make_float4(ray.d.y, ray.d.z, 0.0f, __int_as_float(pix));
+      int coin = 0;
+      if (JT_COIN_QUEUES && SAMPLER == 1) {
+        // index of the next bounce's coin: this counter, + 1 if the probe kernel still plays Russian roulette for this
+        // bounce (p.bounce > 3, src/trace.jl:459), + 2 if the next bounce starts with the medium's distance sampling
+        const unsigned at = p.draw + ((to_probe && p.bounce > 3) ? 1u : 0u) + ((p.flags & WF_F_MEDIUM) ? 2u : 0u);
+        coin = jt_rng_float(rkey, at) < 0.5f ? WF_RAY_COIN : 0;
+      }
+      B.ray1[s] = make_float4(ray.d.y, ray.d.z, __int_as_float(coin), __int_as_float(pix));
       B.wgt[s] = make_float4(weight.x, weight.y, weight.z, 0.0f);
       B.rad[s] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
       wf_store_ctl(B, s, p);
@@ -674,7 +706,7 @@ __global__ void __launch_bounds__(JT_SHADE_BLOCK, JT_SHADE_MINBLOCKS) k_wf_shade
       const int c = B.counts[WF_C_SHADEK(k)];
       const int blocks = (c + JT_SHADE_BLOCK - 1) / JT_SHADE_BLOCK;
       if (key < 0 && (int)blockIdx.x < first_block + blocks) {
-        key = k;
+        key = k == WF_KEY_MISS ? WF_TYPE_MISS : WF_KEY_TYPE(k);  // the body only needs the material type
         const int at = ((int)blockIdx.x - first_block) * JT_SHADE_BLOCK + (int)threadIdx.x;
         if (at < c) s = B.q_shade[(size_t)k * B.n + at];
       }
@@ -692,7 +724,7 @@ __global__ void __launch_bounds__(JT_SHADE_BLOCK, JT_SHADE_MINBLOCKS) k_wf_shade
       case 4: wf_shade_slot<SAMPLER, MODE, 4>(S, B, P, s, key, to_extend, to_probe, cnt); break;
       case 5: wf_shade_slot<SAMPLER, MODE, 5>(S, B, P, s, key, to_extend, to_probe, cnt); break;
       case 6: wf_shade_slot<SAMPLER, MODE, 6>(S, B, P, s, key, to_extend, to_probe, cnt); break;
-      case WF_KEY_MISS: wf_shade_slot<SAMPLER, MODE, WF_KEY_MISS>(S, B, P, s, key, to_extend, to_probe, cnt); break;
+      case WF_TYPE_MISS: wf_shade_slot<SAMPLER, MODE, WF_TYPE_MISS>(S, B, P, s, key, to_extend, to_probe, cnt); break;
       default: break;  // blocks beyond the queues; key 7 (gltfpbr) is rejected at staging
     }
   } else

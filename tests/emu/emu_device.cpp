@@ -200,7 +200,7 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
     int ne = counts[WF_C_EXT(cur)];
     if (p->traversal == 1) run(ne, [&] { k_wf_extend<MODE_REF>(e->dev, B, cur, cnt); });
     else if (jt_emu_suspend_every > 0) {
-      for (int q = 0; q < ne; q++) g_resumed += B.ray1[B.q_ext[cur][q]].z != 0.0f;
+      for (int q = 0; q < ne; q++) g_resumed += (__float_as_int(B.ray1[B.q_ext[cur][q]].z) & WF_RAY_SUSPENDED) != 0;
       run(1, [&] { k_wf_extend_persist(e->dev, B, cur, cnt); });
     } else run(ne, [&] { k_wf_extend<MODE_WIDE>(e->dev, B, cur, cnt); });
     int ns = 0;
