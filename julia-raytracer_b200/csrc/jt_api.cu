@@ -727,6 +727,7 @@ static int wf_prepare(jt_scene* sc, jt_state* st) {
     if ((rc = alloc((void**)&ga, n * 64)) || (rc = alloc((void**)&gb, n * 64)) || (rc = alloc((void**)&gc, n * 32)) ||
         (rc = alloc((void**)&gd, n * 32)) ||
         (rc = alloc((void**)&B.parked, n * JT_SUSPEND_STACK * sizeof(uint2))) ||
+        (rc = alloc((void**)&B.held, (JT_HELD_RESULT ? n * 3 : 1) * sizeof(float4))) ||
         (rc = alloc((void**)&B.q_ext[0], n * 4)) || (rc = alloc((void**)&B.q_ext[1], n * 4)) ||
         (rc = alloc((void**)&B.next_sample, n * 4)) || (rc = alloc((void**)&B.commit, n * 4)) ||
         (rc = alloc((void**)&B.regen, ((n + 15) & ~(size_t)15) + 16)) ||

@@ -94,6 +94,7 @@ struct WfBuffers {
   WfField<float4, 2> med0;  // density.xyz, scanisotropy (only when the scene has volumetric materials)
   WfField<float4, 2> med1;  // scattering.xyz
   uint2* parked;  // JT_SUSPEND_STACK entries per slot: traversal stack of a ray suspended in the extend kernel's tail
+  float4* held;   // 3 per slot: a finished sample set aside until its pixel's turn (wf_regen_slot)
   int* q_ext[2];
   int* next_sample;  // per pixel of this pipeline (index = pixel - pixel_base): next sample index to hand out
   int* commit;       // per pixel: next sample index to accumulate (samples are accumulated in order)
@@ -254,38 +255,97 @@ JT_DEV bool wf_claim(const JtDevScene& S, const WfBuffers& B, const DevParams& P
 
 // k_wf_regen's per-slot work: commit the parked sample when it is the pixel's turn (src/trace.jl:625-648), then find the
 // slot its next sample. `cur` is the extend queue consumed this iteration (victim lookup).
+// One result of a finished sample: committed into the accumulators when it is its pixel's turn.
+struct WfResult {
+  int pix, sample;
+  bool hit;
+  f3 radiance, albedo, normal;
+};
+JT_DEV bool wf_try_commit(const JtDevScene& S, const WfBuffers& B, const DevState& st, const DevParams& P, const WfResult& R,
+                          int epoch) {
+  const int lp = R.pix - B.pixel_base;
+  // every load the commit needs is issued before the turn is examined: one memory round trip instead of two
+  const int turn = B.commit[lp];
+  const float4 old_img = st.image[R.pix], old_alb = st.albedo[R.pix], old_nrm = st.normal[R.pix];
+  const int old_hits = st.hits[R.pix];
+  // an earlier sample of the pixel is still in flight, or was committed by this very launch
+  if ((turn >> 8) != R.sample || (turn & 255) == (epoch & 255)) return false;
+  TraceOut r;
+  r.radiance = R.radiance;
+  r.hit = R.hit;
+  f3 cam_d = f3{0.0f, 0.0f, 0.0f};
+  if (r.hit) {
+    r.albedo = R.albedo;
+    r.normal = R.normal;
+  } else {
+    r.albedo = f3{0.0f, 0.0f, 0.0f};
+    r.normal = f3{0.0f, 0.0f, 0.0f};
+    // the camera ray direction (normal AOV of a miss) is a pure function of the RNG stream: recompute
+    Rng rng{jt_rng_key(P.seed, (uint32_t)R.pix, (uint32_t)R.sample), 0u};
+    f2 puv = rng.next2();
+    f2 luv = rng.next2();
+    cam_d = sample_camera(S.cameras[P.camera], R.pix % P.width, R.pix / P.width, P.width, P.height, puv, luv, P.tentfilter != 0).d;
+  }
+  accumulate_loaded(st, P, S.num_environments != 0, R.pix, R.sample, r, cam_d, old_img, old_alb, old_nrm, old_hits);
+  B.commit[lp] = WF_COMMIT_WORD(R.sample + 1, epoch);
+  return true;
+}
+
+// A slot can hold a SECOND finished sample (WfBuffers::held: 3 x float4 per slot). With several slots on one pixel a
+// sample often finishes before its predecessor; instead of idling until its turn the slot sets the result aside and
+// starts another sample (JT_ITER_LOG on features1: the extend queue ran at 0.5-0.75 fill because of such waits). The
+// slot keeps visiting k_wf_regen (flag WF_FLAG_HELD) until the held result is committed; it only stalls when the next
+// sample ends while the held one is still waiting.
+//   held[0] = {radiance.xyz, bits(pixel)}  held[1] = {albedo.xyz, bits(sample)}  held[2] = {normal.xyz, bits(1 valid | 2 hit)}
+#ifndef JT_HELD_RESULT
+#define JT_HELD_RESULT 0 /* measured: features1 +1 %, classroom -1 % (profiles/r02/tuning_variants.txt item 22) */
+#endif
+#define WF_FLAG_ENDED 1 /* regen flag byte: the slot's current sample ended (set by shade / probe) */
+#define WF_FLAG_HELD 2  /* the slot only has a held result to commit; its current path is in flight */
+
+// k_wf_regen's per-slot work: commit what can be committed (src/trace.jl:625-648), then find the slot its next sample.
+// `cur` is the extend queue consumed this iteration (victim lookup). *flag_out = the slot's regen flag afterwards.
 JT_DEV int wf_regen_slot(const JtDevScene& S, const WfBuffers& B, const DevState& st, const DevParams& P, int s, int cur,
-                         int sample_end, int epoch) {
+                         int sample_end, int epoch, int flag_in, unsigned char* flag_out) {
+  bool held = false;
+#if JT_HELD_RESULT
+  {
+    const float4 h2 = B.held[3 * (size_t)s + 2];
+    const int hbits = __float_as_int(h2.w);
+    if (hbits & 1) {
+      const float4 h0 = B.held[3 * (size_t)s], h1 = B.held[3 * (size_t)s + 1];
+      WfResult R{__float_as_int(h0.w), __float_as_int(h1.w), (hbits & 2) != 0, f3{h0.x, h0.y, h0.z}, f3{h1.x, h1.y, h1.z},
+                 f3{h2.x, h2.y, h2.z}};
+      if (wf_try_commit(S, B, st, P, R, epoch)) B.held[3 * (size_t)s + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      else held = true;
+    }
+  }
+#endif
+  if (!(flag_in & WF_FLAG_ENDED)) {  // the current path is still in flight: nothing else to do
+    *flag_out = held ? WF_FLAG_HELD : 0;
+    return WF_REGEN_RETRY;
+  }
   WfPath p = wf_load_ctl(B, s);
   const int pix = wf_slot_pixel(B, s);
-  const int lp = pix - B.pixel_base;
   if (!(p.flags & WF_F_COMMITTED)) {
-    // every load the commit needs is issued before the turn is examined: one memory round trip instead of four
-    const int turn = B.commit[lp];
     const float4 rad = B.rad[s], a = B.alb[s], n = B.nrm[s];
-    const float4 old_img = st.image[pix], old_alb = st.albedo[pix], old_nrm = st.normal[pix];
-    const int old_hits = st.hits[pix];
-    // an earlier sample of the pixel is still in flight, or was committed by this very launch
-    if ((turn >> 8) != (int)p.sample || (turn & 255) == (epoch & 255)) return WF_REGEN_RETRY;
-    TraceOut r;
-    r.radiance = f3{rad.x, rad.y, rad.z};
-    r.hit = (p.flags & WF_F_HIT) != 0u;
-    f3 cam_d = f3{0.0f, 0.0f, 0.0f};
-    if (r.hit) {
-      r.albedo = f3{a.x, a.y, a.z};
-      r.normal = f3{n.x, n.y, n.z};
-    } else {
-      r.albedo = f3{0.0f, 0.0f, 0.0f};
-      r.normal = f3{0.0f, 0.0f, 0.0f};
-      // the camera ray direction (normal AOV of a miss) is a pure function of the RNG stream: recompute
-      Rng rng{jt_rng_key(P.seed, (uint32_t)pix, p.sample), 0u};
-      f2 puv = rng.next2();
-      f2 luv = rng.next2();
-      cam_d = sample_camera(S.cameras[P.camera], pix % P.width, pix / P.width, P.width, P.height, puv, luv, P.tentfilter != 0).d;
+    WfResult R{pix, (int)p.sample, (p.flags & WF_F_HIT) != 0u, f3{rad.x, rad.y, rad.z}, f3{a.x, a.y, a.z}, f3{n.x, n.y, n.z}};
+    if (!wf_try_commit(S, B, st, P, R, epoch)) {
+#if JT_HELD_RESULT
+      if (!held) {  // set it aside; the slot is free for another sample
+        B.held[3 * (size_t)s] = make_float4(rad.x, rad.y, rad.z, __int_as_float(pix));
+        B.held[3 * (size_t)s + 1] = make_float4(a.x, a.y, a.z, __int_as_float((int)p.sample));
+        B.held[3 * (size_t)s + 2] = make_float4(n.x, n.y, n.z, __int_as_float(1 | (R.hit ? 2 : 0)));
+        held = true;
+      } else
+#endif
+      {
+        *flag_out = WF_FLAG_ENDED;  // both results wait for their turns: the slot stalls
+        return WF_REGEN_RETRY;
+      }
     }
-    accumulate_loaded(st, P, S.num_environments != 0, pix, (int)p.sample, r, cam_d, old_img, old_alb, old_nrm, old_hits);
-    B.commit[lp] = WF_COMMIT_WORD((int)p.sample + 1, epoch);
   }
+  *flag_out = held ? WF_FLAG_HELD : 0;
   if (wf_claim(S, B, P, s, pix, sample_end)) return WF_REGEN_QUEUED;
 #if JT_WORK_STEALING
   if (B.counts[WF_C_ACTIVE] > 0) {
@@ -303,13 +363,19 @@ JT_DEV int wf_regen_slot(const JtDevScene& S, const WfBuffers& B, const DevState
         return WF_REGEN_STOLEN;
       }
     }
-    if (!(p.flags & WF_F_COMMITTED)) {
-      p.flags |= WF_F_COMMITTED;
-      wf_store_ctl(B, s, p);
-    }
-    return WF_REGEN_RETRY;
   }
 #endif
+  // nothing to start: the slot stays flagged as "ended, result taken care of" while a held result or unstarted samples
+  // somewhere keep it busy, and is idle for good otherwise
+  if (!(p.flags & WF_F_COMMITTED)) {
+    p.flags |= WF_F_COMMITTED;
+    wf_store_ctl(B, s, p);
+  }
+  if (held || (JT_WORK_STEALING && B.counts[WF_C_ACTIVE] > 0)) {
+    *flag_out = WF_FLAG_ENDED;
+    return WF_REGEN_RETRY;
+  }
+  *flag_out = 0;
   return WF_REGEN_DONE;
 }
 
@@ -322,6 +388,7 @@ __global__ void __launch_bounds__(256) k_wf_generate(JtDevScene S, WfBuffers B, 
   B.next_sample[s] = sample_begin + 1;
   B.commit[s] = WF_COMMIT_WORD(sample_begin, 255);  // the first k_wf_regen launch has epoch 0
   B.regen[s] = 0;
+  if (JT_HELD_RESULT) B.held[3 * (size_t)s + 2] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   B.q_ext[0][s] = s;
   if (s == 0) {
     for (int k = 0; k < WF_C_TOTAL; k++) B.counts[k] = 0;
@@ -807,7 +874,7 @@ __global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(JtDevScene S, WfBuf
 #pragma unroll
     for (int k = 0; k < WF_REGEN_PER_THREAD / 4; k++)
 #pragma unroll
-      for (int j = 0; j < 4; j++) flags |= ((w[k] >> (8 * j)) & 1u) << (4 * k + j);
+      for (int j = 0; j < 4; j++) flags |= (((w[k] >> (8 * j)) & 3u) != 0u ? 1u : 0u) << (4 * k + j);
   } else {
     for (int i = 0; i < WF_REGEN_PER_THREAD && first + i < B.n; i++)
       if (B.regen[first + i]) flags |= 1u << i;
@@ -843,8 +910,10 @@ __global__ void __launch_bounds__(WF_REGEN_BLOCK) k_wf_regen(JtDevScene S, WfBuf
     int slot = -1, what = 0;
     if (j < total) {
       slot = flagged[j];
-      what = wf_regen_slot(S, B, st, P, slot, cur, sample_end, epoch);
-      if (what != WF_REGEN_RETRY) B.regen[slot] = 0;
+      const int flag_in = B.regen[slot];
+      unsigned char flag_out = 0;
+      what = wf_regen_slot(S, B, st, P, slot, cur, sample_end, epoch, flag_in, &flag_out);
+      if (flag_out != (unsigned char)flag_in) B.regen[slot] = flag_out;
       done += what == WF_REGEN_DONE;
       stolen += what == WF_REGEN_STOLEN;
     }

@@ -188,6 +188,8 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
   B.parked = parked.data();
   std::vector<int> next_sample(n), commit(n);
   B.next_sample = next_sample.data(); B.commit = commit.data();
+  std::vector<float4> held((size_t)3 * n, float4{0, 0, 0, 0});
+  B.held = held.data();
   B.counts = counts.data(); B.n = n; B.pixel_base = 0;
   unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   auto run = [&](int threads, auto&& kernel) {
@@ -219,8 +221,9 @@ EMU_API int emu_trace_wavefront(void* h, const jt_params* p, int width, int heig
     // k_wf_regen, sequentially: flagged slots in slot order -> commit, claim, queue; counters recycled
     for (int sl = 0; sl < n; sl++)
       if (regen[sl]) {
-        int what = wf_regen_slot(e->dev, B, st, P, sl, cur, end, iterations);
-        if (what != WF_REGEN_RETRY) regen[sl] = 0;
+        unsigned char flag_out = 0;
+        int what = wf_regen_slot(e->dev, B, st, P, sl, cur, end, iterations, regen[sl], &flag_out);
+        regen[sl] = flag_out;
         if (what == WF_REGEN_QUEUED || what == WF_REGEN_STOLEN) B.q_ext[next][B.counts[WF_C_EXT(next)]++] = sl;
         if (what == WF_REGEN_DONE) counts[WF_C_DONE]++;
       }
