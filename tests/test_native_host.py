@@ -396,3 +396,45 @@ def test_main_with_native_host(synth_dir, tmp_path):
     r2 = jm.main(args + f"--gpu-native-host true --output {tmp_path / 'b.png'}")
     assert np.array_equal(r1["image"], r2["image"])
     assert (tmp_path / "a.png").read_bytes() == (tmp_path / "b.png").read_bytes()
+
+
+def _build_c_host(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "jtrace_c")
+    libdir = os.path.join(root, "julia-raytracer_b200")
+    subprocess.check_call(["gcc", "-O2", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "examples", "jtrace_c.c"), "-o", exe, "-L" + libdir, "-ljtrace_b200",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_c_host_example_builds_and_fails_loudly_without_a_gpu(synth_dir, tmp_path):
+    """examples/jtrace_c.c: a host in plain C over include/jtrace_b200.h alone. Without a CUDA device the library refuses
+    (JT_ERR_NO_DEVICE): there is no CPU fallback to fall into."""
+    import subprocess
+    _lib.lib()
+    exe = _build_c_host(tmp_path)
+    if _lib.lib().jt_device_count() > 0:
+        pytest.skip("a GPU is present: covered by the gpu test")
+    r = subprocess.run([exe, synth_dir, str(tmp_path / "o.ppm"), "32", "1"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CUDA device" in r.stderr, (r.returncode, r.stderr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("device_lights", [0, 1])
+def test_c_host_example_renders_the_same_image(synth_dir, tmp_path, device_lights):
+    """The C host and the Python host are two bindings of one ABI: same scene file, same parameters, same bytes."""
+    import subprocess
+    jm = importlib.import_module("julia-raytracer_b200.jtrace")
+    exe = _build_c_host(tmp_path)
+    out = tmp_path / "c.ppm"
+    r = subprocess.run([exe, synth_dir, str(out), "96", "3", "1", str(device_lights)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    head, size, maxv, body = out.read_bytes().split(b"\n", 3)
+    w, h = (int(x) for x in size.split())
+    assert head == b"P6" and maxv == b"255" and len(body) == 3 * w * h
+    res = jm.main(f"--scene {synth_dir} --resolution 96 --samples 3 --batch 1 --output {tmp_path / 'py.png'}")
+    srgb = res["state"].srgb8()
+    assert srgb.shape == (h, w, 4)
+    assert np.array_equal(np.frombuffer(body, np.uint8).reshape(h, w, 3), srgb[..., :3])
