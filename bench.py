@@ -304,8 +304,11 @@ def main():
     # N1: the first upload builds the wide BVH and stores it in the cache directory; for scenes whose build takes long
     # (ecosys: 16.8 M flattened records) the upload is repeated once to time the cached path as well
     cache_dir = os.environ.get("JT_BVH_CACHE_DIR") or os.path.join(tempfile.gettempdir(), "jtrace_b200_bvh_cache")
-    os.makedirs(cache_dir, exist_ok=True)
-    trace.set_bvh_cache_dir(cache_dir)
+    try:
+        os.makedirs(cache_dir, exist_ok=True)
+        trace.set_bvh_cache_dir(cache_dir)
+    except OSError:
+        trace.set_bvh_cache_dir(None)  # nowhere to cache: every upload builds
     t0 = time.perf_counter()
     dscene = trace.DeviceScene(scene, sbvh, lts, local_rank)
     upload_s = time.perf_counter() - t0
