@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--spp-per-step", type=int, default=512)
     ap.add_argument("--traversal", default="wide", choices=["wide", "reference"])
     ap.add_argument("--integrator", default="wavefront", choices=["wavefront", "megakernel"])
-    ap.add_argument("--cpu-spp", type=int, default=2, help="samples per pixel of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-spp", type=int, default=16, help="samples per pixel of the bounded CPU-baseline sample (16 spp of the full image = ~12 s on 16 threads)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong-spp", type=int, default=512, help="total samples per step of the strong-scaling leg (N > 1)")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the strong-scaling and in-library-group legs")
