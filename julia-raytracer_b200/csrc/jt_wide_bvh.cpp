@@ -70,10 +70,10 @@ struct Rec {  // one leaf record + its reference visit ranks
   uint32_t rank[8];
 };
 
-struct BNode {  // intermediate binary tree
-  Box3 box;
-  int left = -1, right = -1;  // children (internal)
-  int first = 0, count = 0;   // records (leaf, count <= 3)
+struct BNode {  // intermediate binary tree. No default initialisers: the node array of a flattened scene is 1.4 GB and
+  Box3 box;     // is sized up front; every creation site writes all five fields
+  int left, right;   // children (internal), -1 / -1 for a leaf
+  int first, count;  // records (leaf, count <= 3)
   bool leaf() const { return left < 0; }
 };
 
@@ -85,15 +85,15 @@ struct Ref {  // what the SAH build streams and partitions in place: box + recor
 enum { NODE_CHUNK = 256, TASK_MIN = 8192 };
 
 struct Tree {
-  std::vector<Rec> recs;
+  JtBigVec<Rec> recs;  // (JtBigVec: resize() does not zero -- these are GB-sized for a flattened scene)
   // filled by the (multi-threaded) SAH build: storage is sized up front, slots are handed out atomically
-  std::vector<BNode> nodes;
-  std::vector<int> leaf_store;  // record ids of the leaves, contiguous per leaf
+  JtBigVec<BNode> nodes;
+  JtBigVec<int> leaf_store;  // record ids of the leaves, contiguous per leaf
   std::atomic<int> next_node{0}, next_leaf{0};
   void reserve_for(size_t nrecs) {
     // 2n - 1 nodes at most, plus the tails of the per-task allocation chunks (NodeChunk)
     nodes.resize(2 * nrecs + 1 + NODE_CHUNK * (2 * nrecs / TASK_MIN + 64));
-    leaf_store.assign(nrecs, 0);
+    leaf_store.resize(nrecs);
     next_node = 0;
     next_leaf = 0;
   }
@@ -215,8 +215,9 @@ class Collapser {
   // ecosys is 16.8 M records).
   int sah_root(const std::vector<int>& recs, Tree& t) {
     if (recs.empty()) return -1;
-    std::vector<Ref> refs(recs.size());
-    for (size_t i = 0; i < recs.size(); i++) {
+    JtBigVec<Ref> refs(recs.size());
+#pragma omp parallel for schedule(static) if ((int64_t)recs.size() > parallel_min_) num_threads(build_threads_)
+    for (long i = 0; i < (long)recs.size(); i++) {
       const Box3& b = t.recs[(size_t)recs[i]].box;
       for (int k = 0; k < 3; k++) {
         refs[i].lo[k] = b.lo[k];
@@ -477,6 +478,7 @@ class Collapser {
     BNode& in = t.nodes[(size_t)id];
     in.left = l;
     in.right = r;
+    in.first = in.count = 0;
     in.box = t.nodes[(size_t)l].box;
     in.box.add(t.nodes[(size_t)r].box);
     return id;
@@ -974,9 +976,7 @@ class Collapser {
       int root = sah_root(recs, t);
       out_->shape_root[s] = emit(t, root);
     }
-    // top level: ONE surface-area tree over every triangle of the identity-frame instances (inlined: the
-    // two-level structure is pure overhead for them) plus one reference record per
-    // remaining instance. Order follows the reference TLAS only through the rank tables.
+    if (verbose) fprintf(stderr, "jt_build_wide: %zu BLAS in %.2f s\n", shapes_.size(), now() - tb0);
     visit_ranks(tlas_nodes, tlas_prims, (int64_t)insts_.size(), out_->inst_rank);
     Tree t;
     std::vector<int> top;

@@ -237,3 +237,4 @@ def test_work_stealing_keeps_the_sample_order(pair, name, sampler, traversal):
     # split ranges (every range restarts the claim / commit counters) give the same accumulators
     a = e.trace(p, w, h, 0, 12, wavefront=True)
     assert np.array_equal(a["image"], got["image"])
+
